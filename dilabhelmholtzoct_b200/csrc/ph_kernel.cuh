@@ -1,0 +1,272 @@
+// Cubical persistence of a batch of maps: one CTA per (image, class) map.
+//
+// Replaces gudhi's sort-all-cells + persistent-cohomology reduction (reached from
+// /root/reference/octsam/models/topological_loss.py:62-63) by a lock-free, sort-free scheme:
+//
+//   level 0  every node unions with the far end of its EARLIEST incident edge whenever that
+//            edge has the node's own value (a zero-persistence merge).  Elder-linked lock-free
+//            union-find (CAS on the younger root).  This contracts the grid to its basins.
+//   level 1  every remaining edge is merged into a triplet merge tree
+//            T[y] = (edge at which y's component dies, an elder node it merges into)
+//            with the order-independent, CAS-based Merge of Smirnov & Morozov ("Triplet merge
+//            trees"): edges may arrive in any order and from any thread; the fixed point is the
+//            elder-rule pairing of the sequential Kruskal scan.
+//   emit     every level-0 root y with a recorded edge is one persistence pair; zero-persistence
+//            pairs are dropped (gudhi min_persistence = 0, strict).
+//
+// All comparisons use the exact cell order (value, bitmap position), so persistence pairs and
+// critical pixels are bit-exact under ties.
+#pragma once
+#include "tl_common.cuh"
+
+namespace tl {
+
+constexpr int kPhThreads = 1024;
+
+struct PhArgs {
+    const float* maps[2];   // set 0 (pred) / set 1 (truth); maps[1] may be null when n_sets == 1
+    PairRec* pairs[2];      // [n_maps][cap]
+    uint64_t* skeys[2];     // [n_maps][cap] sort key of each emitted pair (death-cell order), may be null
+    int32_t* counts[2];     // [n_maps]
+    int n_sets, n_maps, H, W, cap;
+    uint64_t* T;            // [gridDim.x][t_stride]
+    size_t t_stride;
+    unsigned int* job_counter;
+};
+
+template <int DIM>
+struct Ph {
+    Geo<DIM> g;
+    uint64_t* T;
+
+    __device__ __forceinline__ Ph(const float* f, int H, int W, uint64_t* T_) : g(f, H, W), T(T_) {}
+
+    __device__ __forceinline__ int find0(int x) const {
+        for (;;) {
+            uint64_t t = ld_cg_u64(T + x);
+            if ((uint32_t)(t >> 32) != kCodeL0) return x;
+            x = (int)(uint32_t)t;
+        }
+    }
+
+    // level-0 union: link the younger root under the elder one
+    __device__ void union0(int a, int b) {
+        for (;;) {
+            int ra = find0(a), rb = find0(b);
+            if (ra == rb) return;
+            if (g.nkey(rb) < g.nkey(ra)) { int t = ra; ra = rb; rb = t; }
+            unsigned long long expect = ((unsigned long long)kCodeRoot << 32) | (uint32_t)rb;
+            unsigned long long want = ((unsigned long long)kCodeL0 << 32) | (uint32_t)ra;
+            unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(T + rb), expect, want);
+            if (old == expect) return;
+            a = ra; b = rb;
+        }
+    }
+
+    // representative of x at level skey: follow entries merged at or before skey
+    __device__ __forceinline__ int rep(int x, uint64_t skey, uint64_t& entry) const {
+        for (;;) {
+            uint64_t t = ld_cg_u64(T + x);
+            uint32_t code = (uint32_t)(t >> 32);
+            if (code == kCodeRoot) { entry = t; return x; }
+            if (code != kCodeL0 && g.ekey(code - 1) > skey) { entry = t; return x; }
+            x = (int)(uint32_t)t;
+        }
+    }
+
+    // triplet-merge-tree Merge(a, edge, b), lock-free
+    __device__ void merge(int a, int b, uint32_t pos, uint64_t skey) {
+        uint32_t code = pos + 1;
+        for (;;) {
+            uint64_t ta, tb;
+            int x = rep(a, skey, ta), y = rep(b, skey, tb);
+            if (x == y) return;
+            if (g.nkey(y) < g.nkey(x)) { int t = x; x = y; y = t; tb = ta; }
+            // y is the younger representative: it dies at this edge into x
+            unsigned long long want = ((unsigned long long)code << 32) | (uint32_t)x;
+            unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(T + y),
+                                               (unsigned long long)tb, want);
+            if (old == tb) {
+                uint32_t ocode = (uint32_t)(tb >> 32);
+                if (ocode == kCodeRoot) return;
+                // y used to die at `ocode` into b': re-assert that connection for x
+                a = x; b = (int)(uint32_t)tb; code = ocode; skey = g.ekey(ocode - 1);
+            } else {
+                a = x; b = y;
+            }
+        }
+    }
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
+    __shared__ unsigned int s_job;
+    __shared__ int s_count;
+    __shared__ unsigned long long s_argmax;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int H = A.H, W = A.W, N = H * W;
+    uint64_t* T = A.T + (size_t)blockIdx.x * A.t_stride;
+    const unsigned int n_jobs = (unsigned)A.n_sets * (unsigned)A.n_maps;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_job = atomicAdd(A.job_counter, 1u); s_count = 0; s_argmax = 0ull; }
+        __syncthreads();
+        const unsigned int job = s_job;
+        if (job >= n_jobs) break;
+        const int set = (int)(job % (unsigned)A.n_sets), map = (int)(job / (unsigned)A.n_sets);
+        Ph<DIM> ph(A.maps[set] + (size_t)map * N, H, W, T);
+        const Geo<DIM>& g = ph.g;
+        const int NN = g.NN, GW = g.GW, VW = g.VW;
+
+        // ---- phase 0: every node is its own root
+        for (int x = tid; x < NN; x += nt) T[x] = ((uint64_t)kCodeRoot << 32) | (uint32_t)x;
+        if (DIM == 0) {  // argmax(f), first in raster order: torch_topological's fake destroyer
+            unsigned long long best = 0ull;
+            for (int p = tid; p < N; p += nt) {
+                unsigned long long k = ((unsigned long long)mono32(__ldg(g.f + p)) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)p);
+                best = k > best ? k : best;
+            }
+            atomicMax(&s_argmax, best);
+        }
+        __syncthreads();
+
+        // ---- phase 1: level-0 contraction along each node's earliest incident edge
+        const int n_real = DIM == 1 ? N : NN;
+        for (int x = tid; x < n_real; x += nt) {
+            uint64_t best = ~0ull;
+            int other = -1;
+            if (DIM == 1) {
+                const int r = x / W, c = x - r * W;
+                const float fp = g.px(r, c);
+                // top, bottom: h-edges; left, right: v-edges
+                {
+                    float v = r == 0 ? fp : fminf(fp, g.px(r - 1, c));
+                    uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 1 + (2 * r) * GW));
+                    if (k < best) { best = k; other = r == 0 ? g.OUT : x - W; }
+                }
+                {
+                    float v = r == H - 1 ? fp : fminf(fp, g.px(r + 1, c));
+                    uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 1 + (2 * r + 2) * GW));
+                    if (k < best) { best = k; other = r == H - 1 ? g.OUT : x + W; }
+                }
+                {
+                    float v = c == 0 ? fp : fminf(fp, g.px(r, c - 1));
+                    uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + (2 * r + 1) * GW));
+                    if (k < best) { best = k; other = c == 0 ? g.OUT : x - 1; }
+                }
+                {
+                    float v = c == W - 1 ? fp : fminf(fp, g.px(r, c + 1));
+                    uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 2 + (2 * r + 1) * GW));
+                    if (k < best) { best = k; other = c == W - 1 ? g.OUT : x + 1; }
+                }
+                if ((uint32_t)(best >> 32) != (uint32_t)(g.make_ekey(fp, 0u) >> 32)) other = -1;  // strict local max
+            } else {
+                const int i = x / VW, j = x - i * VW;
+                if (i > 0) {
+                    uint64_t k = g.make_ekey(g.vedge_val(i - 1, j), (uint32_t)(2 * j + (2 * i - 1) * GW));
+                    if (k < best) { best = k; other = x - VW; }
+                }
+                if (i < H) {
+                    uint64_t k = g.make_ekey(g.vedge_val(i, j), (uint32_t)(2 * j + (2 * i + 1) * GW));
+                    if (k < best) { best = k; other = x + VW; }
+                }
+                if (j > 0) {
+                    uint64_t k = g.make_ekey(g.hedge_val(i, j - 1), (uint32_t)(2 * j - 1 + (2 * i) * GW));
+                    if (k < best) { best = k; other = x - 1; }
+                }
+                if (j < W) {
+                    uint64_t k = g.make_ekey(g.hedge_val(i, j), (uint32_t)(2 * j + 1 + (2 * i) * GW));
+                    if (k < best) { best = k; other = x + 1; }
+                }
+                // a vertex always has an incident edge of its own value (min of the same pixels)
+            }
+            if (other >= 0) ph.union0(x, other);
+        }
+        __syncthreads();
+        // flatten level-0 chains so that later finds are one hop
+        for (int x = tid; x < n_real; x += nt) {
+            int r = ph.find0(x);
+            if (r != x) T[x] = ((uint64_t)kCodeL0 << 32) | (uint32_t)r;
+        }
+        __syncthreads();
+
+        // ---- phase 2: all edges into the triplet merge tree
+        const int n_vedges = H * (W + 1), n_hedges = (H + 1) * W;
+        for (int e = tid; e < n_vedges + n_hedges; e += nt) {
+            int a, b;
+            uint32_t pos;
+            float val;
+            if (e < n_vedges) {
+                const int i = e / (W + 1), j = e - i * (W + 1);
+                pos = (uint32_t)(2 * j + (2 * i + 1) * GW);
+                val = g.vedge_val(i, j);
+                if (DIM == 1) { a = j == 0 ? g.OUT : i * W + j - 1; b = j == W ? g.OUT : i * W + j; }
+                else { a = i * VW + j; b = a + VW; }
+            } else {
+                const int e2 = e - n_vedges, i = e2 / W, j = e2 - i * W;
+                pos = (uint32_t)(2 * j + 1 + (2 * i) * GW);
+                val = g.hedge_val(i, j);
+                if (DIM == 1) { a = i == 0 ? g.OUT : (i - 1) * W + j; b = i == H ? g.OUT : i * W + j; }
+                else { a = i * VW + j; b = a + 1; }
+            }
+            // quick reject: same level-0 basin
+            uint64_t ta = ld_cg_u64(T + a), tb = ld_cg_u64(T + b);
+            int la = (uint32_t)(ta >> 32) == kCodeL0 ? (int)(uint32_t)ta : a;
+            int lb = (uint32_t)(tb >> 32) == kCodeL0 ? (int)(uint32_t)tb : b;
+            if (la == lb) continue;
+            ph.merge(la, lb, pos, g.make_ekey(val, pos));
+        }
+        __syncthreads();
+
+        // ---- phase 3: emit pairs of positive persistence
+        PairRec* out = A.pairs[set] + (size_t)map * A.cap;
+        uint64_t* skeys = A.skeys[set] ? A.skeys[set] + (size_t)map * A.cap : nullptr;
+        for (int x0 = 0; x0 < NN; x0 += nt) {
+            const int x = x0 + tid;
+            bool emit = false;
+            PairRec rec;
+            uint64_t sk = 0;
+            if (x < NN) {
+                const uint64_t t = T[x];
+                const uint32_t code = (uint32_t)(t >> 32);
+                if (code != kCodeL0 && code != kCodeRoot) {
+                    const uint32_t pos = code - 1;
+                    const uint64_t ek = g.ekey(pos), nk = g.nkey(x);
+                    if ((uint32_t)(ek >> 32) != (uint32_t)(nk >> 32)) {
+                        emit = true;
+                        if (DIM == 1) { rec.cre = g.edge_top(pos); rec.des = x; sk = ~nk; }  // death cell = square x
+                        else { g.vertex_val(x / VW, x % VW, &rec.cre); rec.des = g.edge_top(pos); sk = ek; }  // death cell = edge
+                    }
+                } else if (DIM == 0 && code == kCodeRoot) {  // the essential class, emitted last
+                    emit = true;
+                    g.vertex_val(x / VW, x % VW, &rec.cre);
+                    rec.des = (int)(0xFFFFFFFFu - (uint32_t)s_argmax);
+                    sk = ~0ull;
+                }
+            }
+            // warp-aggregated slot allocation
+            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, emit);
+            if (ballot) {
+                int base = 0;
+                const int lane = tid & 31, leader = __ffs(ballot) - 1;
+                if (lane == leader) base = atomicAdd(&s_count, __popc(ballot));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (emit) {
+                    const int slot = base + __popc(ballot & lanemask_lt());
+                    if (slot < A.cap) {
+                        rec.b = __ldg(g.f + rec.cre);
+                        rec.d = __ldg(g.f + rec.des);
+                        rec.tb = rec.td = __int_as_float(0x7FC00000);
+                        out[slot] = rec;
+                        if (skeys) skeys[slot] = sk;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) A.counts[set][map] = s_count;
+    }
+}
+
+}  // namespace tl

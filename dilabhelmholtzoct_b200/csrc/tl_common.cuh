@@ -1,0 +1,124 @@
+// Shared device helpers for the topological-loss kernels (sm_100a).
+//
+// Geometry and ordering follow the gudhi cubical complex the reference reaches through
+// torch_topological (reference call site /root/reference/octsam/models/topological_loss.py:55-63;
+// cell semantics in SURVEY.md section 8a-note):
+//   * pixels are the 2-cells of a (2H+1)x(2W+1) bitmap; an edge/vertex takes the min of its cofaces;
+//   * total order of cells: (value, dimension, bitmap position);
+//   * H0 = elder-rule union-find on the vertex graph, edges ascending;
+//   * H1 = elder-rule union-find on the dual graph (squares + OUTSIDE), edges descending
+//     (2-D Alexander duality).
+// Both are expressed in ONE ascending form: for H1 every key is bit-complemented, so
+// "smaller key" always means "earlier in the scan" (edges) / "elder" (nodes).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tl {
+
+struct __align__(8) PairRec {
+    int32_t cre, des;  // creator / destroyer pixel (flat r*W+c)
+    float b, d;        // diagram point gathered from the map: (f[cre], f[des])
+    float tb, td;      // matched ground-truth point, NaN = matched to the diagonal (pred side only)
+};
+
+__device__ __forceinline__ uint32_t mono32(float f) {
+    uint32_t u = __float_as_uint(f);
+    if (u == 0x80000000u) u = 0u;  // -0.0 == +0.0 in the reference's double compare
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t* p) {
+    return __ldcg(reinterpret_cast<const unsigned long long*>(p));
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Triplet-table entry: high 32 bits = merge code, low 32 bits = target node.
+//   code 0            : level-0 link (merged before every recorded edge; always followed)
+//   code 0xFFFFFFFF   : root (never merged)
+//   otherwise         : bitmap position of the merging edge + 1
+constexpr uint32_t kCodeL0 = 0u;
+constexpr uint32_t kCodeRoot = 0xFFFFFFFFu;
+
+template <int DIM>
+struct Geo {
+    const float* f;
+    int H, W, GW, VW, NN, OUT;
+
+    __device__ __forceinline__ Geo(const float* f_, int H_, int W_)
+        : f(f_), H(H_), W(W_), GW(2 * W_ + 1), VW(W_ + 1),
+          NN(DIM == 1 ? H_ * W_ + 1 : (H_ + 1) * (W_ + 1)), OUT(H_ * W_) {}
+
+    __device__ __forceinline__ float px(int r, int c) const { return __ldg(f + r * W + c); }
+
+    // v-edge(i,j): between pixels (i,j-1),(i,j), j in [0,W]; h-edge(i,j): between (i-1,j),(i,j), i in [0,H]
+    __device__ __forceinline__ float vedge_val(int i, int j) const {
+        if (j == 0) return px(i, 0);
+        if (j == W) return px(i, W - 1);
+        return fminf(px(i, j - 1), px(i, j));
+    }
+    __device__ __forceinline__ float hedge_val(int i, int j) const {
+        if (i == 0) return px(0, j);
+        if (i == H) return px(H - 1, j);
+        return fminf(px(i - 1, j), px(i, j));
+    }
+    __device__ __forceinline__ int vedge_top(int i, int j) const {
+        if (j == 0) return i * W;
+        if (j == W) return i * W + W - 1;
+        float a = px(i, j - 1), b = px(i, j);
+        return a <= b ? i * W + j - 1 : i * W + j;  // left pixel if it attains the min
+    }
+    __device__ __forceinline__ int hedge_top(int i, int j) const {
+        if (i == 0) return j;
+        if (i == H) return (H - 1) * W + j;
+        float a = px(i - 1, j), b = px(i, j);
+        return a <= b ? (i - 1) * W + j : i * W + j;  // upper pixel if it attains the min
+    }
+    // vertex (i,j): min over the <=4 surrounding pixels and the first raster pixel attaining it
+    __device__ __forceinline__ float vertex_val(int i, int j, int* top) const {
+        float best = 0.f;
+        int bi = -1;
+#pragma unroll
+        for (int di = -1; di <= 0; ++di)
+#pragma unroll
+            for (int dj = -1; dj <= 0; ++dj) {
+                int r = i + di, c = j + dj;
+                if (r < 0 || r >= H || c < 0 || c >= W) continue;
+                float v = px(r, c);
+                if (bi < 0 || v < best) { best = v; bi = r * W + c; }
+            }
+        if (top) *top = bi;
+        return best;
+    }
+
+    __device__ __forceinline__ uint64_t make_ekey(float val, uint32_t pos) const {
+        uint64_t k = ((uint64_t)mono32(val) << 32) | pos;
+        return DIM == 1 ? ~k : k;
+    }
+    __device__ __forceinline__ float edge_val(uint32_t pos) const {
+        int Y = pos / GW, X = pos - Y * GW;
+        return (Y & 1) ? vedge_val(Y >> 1, X >> 1) : hedge_val(Y >> 1, X >> 1);
+    }
+    __device__ __forceinline__ uint64_t ekey(uint32_t pos) const { return make_ekey(edge_val(pos), pos); }
+    __device__ __forceinline__ int edge_top(uint32_t pos) const {
+        int Y = pos / GW, X = pos - Y * GW;
+        return (Y & 1) ? vedge_top(Y >> 1, X >> 1) : hedge_top(Y >> 1, X >> 1);
+    }
+    // node key: smaller = elder
+    __device__ __forceinline__ uint64_t nkey(int x) const {
+        if (DIM == 1) {
+            if (x == OUT) return 0ull;
+            return ~(((uint64_t)mono32(__ldg(f + x)) << 32) | (uint32_t)x);
+        } else {
+            int i = x / VW, j = x - i * VW;
+            return ((uint64_t)mono32(vertex_val(i, j, nullptr)) << 32) | (uint32_t)x;
+        }
+    }
+};
+
+}  // namespace tl

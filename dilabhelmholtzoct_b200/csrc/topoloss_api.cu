@@ -1,0 +1,310 @@
+// C ABI of libtopoloss.so (see include/topoloss.h for the contract and the reference
+// interface each entry point replaces).  Host side: argument checks, workspace carving and
+// kernel launches on the caller's stream.  No device allocation, no host synchronisation.
+#include "../../include/topoloss.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "match_kernel.cuh"
+#include "ph_kernel.cuh"
+#include "seg_sort.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define TL_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) return fail(TL_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int kPhSlots = 296;     // CTAs of the persistence kernel (2 per SM on a 148-SM B200)
+constexpr int kSortSlots = 296;
+constexpr int kMatchSlots = 296;
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+int max_pairs(int H, int W, int dim) {
+    // one pair per level-0 root at most; roots are strict local extrema or mutual picks (<= nodes/2 + 1)
+    const long long nn = dim == 1 ? (long long)H * W + 1 : (long long)(H + 1) * (W + 1);
+    return (int)(nn / 2 + 2);
+}
+
+struct Layout {
+    int M, cap, n_nodes;
+    size_t counter, counts[2], cost, tpers, coef, pairs[2], skeys[2], match1;
+    size_t T, t_stride;
+    size_t key_tmp, idx_a, idx_b, rec_tmp;
+    size_t v, minv, u, way, pcol, used, stride_c, stride_r;
+    size_t total;
+};
+
+// Carve the workspace.  n_sets = 2 for the loss (pred + truth), 1 for tl_persistence_pairs.
+Layout make_layout(int M, int H, int W, int dim, int B) {
+    Layout L;
+    memset(&L, 0, sizeof(L));
+    L.M = M;
+    L.cap = max_pairs(H, W, dim);
+    L.n_nodes = dim == 1 ? H * W + 1 : (H + 1) * (W + 1);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes); return at; };
+    L.counter = take(256);
+    for (int s = 0; s < 2; ++s) L.counts[s] = take(sizeof(int32_t) * (size_t)M);
+    L.cost = take(sizeof(double) * (size_t)M);
+    L.tpers = take(sizeof(double) * (size_t)M);
+    L.coef = take(sizeof(double) * (size_t)(B > 0 ? B : 1));
+    for (int s = 0; s < 2; ++s) L.pairs[s] = take(sizeof(tl::PairRec) * (size_t)M * L.cap);
+    for (int s = 0; s < 2; ++s) L.skeys[s] = take(sizeof(uint64_t) * (size_t)M * L.cap);
+    L.match1 = take(sizeof(int32_t) * (size_t)M * L.cap);
+    L.t_stride = align_up(sizeof(uint64_t) * (size_t)L.n_nodes) / sizeof(uint64_t);
+    L.T = take(sizeof(uint64_t) * L.t_stride * kPhSlots);
+    L.key_tmp = take(sizeof(uint64_t) * (size_t)L.cap * kSortSlots);
+    L.idx_a = take(sizeof(uint32_t) * (size_t)L.cap * kSortSlots);
+    L.idx_b = take(sizeof(uint32_t) * (size_t)L.cap * kSortSlots);
+    L.rec_tmp = take(sizeof(tl::PairRec) * (size_t)L.cap * kSortSlots);
+    L.stride_c = align_up((size_t)2 * L.cap + 2, 32);
+    L.stride_r = align_up((size_t)L.cap + 2, 32);
+    L.v = take(sizeof(double) * L.stride_c * kMatchSlots);
+    L.minv = take(sizeof(double) * L.stride_c * kMatchSlots);
+    L.u = take(sizeof(double) * L.stride_r * kMatchSlots);
+    L.way = take(sizeof(int32_t) * L.stride_c * kMatchSlots);
+    L.pcol = take(sizeof(int32_t) * L.stride_c * kMatchSlots);
+    L.used = take(L.stride_c * kMatchSlots);
+    L.total = o;
+    return L;
+}
+
+int check_shape(int B, int C, int H, int W, int feat_d) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(TL_ERR_ARG, "bad shape [%d,%d,%d,%d]", B, C, H, W);
+    if (feat_d != 0 && feat_d != 1) return fail(TL_ERR_ARG, "feat_d must be 0 or 1 on 2-D maps, got %d", feat_d);
+    if (H != W) return fail(TL_ERR_ARG, "non-square maps are not supported (H=%d, W=%d)", H, W);
+    if ((long long)(2 * H + 1) * (2 * W + 1) >= 0x7FFFFFF0LL) return fail(TL_ERR_ARG, "map too large");
+    if ((long long)B * C > (1 << 24)) return fail(TL_ERR_ARG, "too many maps");
+    return TL_OK;
+}
+
+template <typename T>
+T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
+
+int launch_ph(const float* m0, const float* m1, int n_sets, const Layout& L, int H, int W, int dim,
+              void* ws, cudaStream_t st) {
+    tl::PhArgs a;
+    a.maps[0] = m0; a.maps[1] = m1;
+    for (int s = 0; s < 2; ++s) {
+        a.pairs[s] = at<tl::PairRec>(ws, L.pairs[s]);
+        a.skeys[s] = at<uint64_t>(ws, L.skeys[s]);
+        a.counts[s] = at<int32_t>(ws, L.counts[s]);
+    }
+    a.n_sets = n_sets; a.n_maps = L.M; a.H = H; a.W = W; a.cap = L.cap;
+    a.T = at<uint64_t>(ws, L.T); a.t_stride = L.t_stride;
+    a.job_counter = at<unsigned int>(ws, L.counter);
+    TL_CUDA(cudaMemsetAsync(a.job_counter, 0, 256, st));
+    long long jobs = (long long)n_sets * L.M;
+    int grid = (int)(jobs < kPhSlots ? jobs : kPhSlots);
+    if (dim == 1) tl::ph_kernel<1><<<grid, tl::kPhThreads, 0, st>>>(a);
+    else tl::ph_kernel<0><<<grid, tl::kPhThreads, 0, st>>>(a);
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+int launch_sort(int n_sets, const Layout& L, void* ws, cudaStream_t st) {
+    tl::SortArgs a;
+    for (int s = 0; s < 2; ++s) {
+        a.pairs[s] = at<tl::PairRec>(ws, L.pairs[s]);
+        a.skeys[s] = at<uint64_t>(ws, L.skeys[s]);
+        a.counts[s] = at<int32_t>(ws, L.counts[s]);
+    }
+    a.n_sets = n_sets; a.n_maps = L.M; a.cap = L.cap;
+    a.key_tmp = at<uint64_t>(ws, L.key_tmp);
+    a.idx_a = at<uint32_t>(ws, L.idx_a);
+    a.idx_b = at<uint32_t>(ws, L.idx_b);
+    a.rec_tmp = at<tl::PairRec>(ws, L.rec_tmp);
+    long long jobs = (long long)n_sets * L.M;
+    int grid = (int)(jobs < kSortSlots ? jobs : kSortSlots);
+    tl::seg_sort_kernel<<<grid, tl::kSortThreads, 0, st>>>(a);
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+void fill_match_scratch(tl::MatchArgs& a, void* ws, size_t v, size_t minv, size_t u, size_t way, size_t pcol,
+                        size_t used, size_t stride_c, size_t stride_r) {
+    a.v = at<double>(ws, v); a.minv = at<double>(ws, minv); a.u = at<double>(ws, u);
+    a.way = at<int32_t>(ws, way); a.pcol = at<int32_t>(ws, pcol); a.used = at<uint8_t>(ws, used);
+    a.stride_c = stride_c; a.stride_r = stride_r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tl_version(void) { return TL_ABI_VERSION; }
+
+const char* tl_last_error(void) { return g_err; }
+
+int tl_max_pairs(int H, int W, int dim) {
+    if (H <= 0 || W <= 0 || (dim != 0 && dim != 1)) return fail(TL_ERR_ARG, "bad arguments");
+    return max_pairs(H, W, dim);
+}
+
+int tl_workspace_bytes(int B, int C, int H, int W, int feat_d, size_t* bytes) {
+    if (!bytes) return fail(TL_ERR_ARG, "bytes is null");
+    int rc = check_shape(B, C, H, W, feat_d);
+    if (rc != TL_OK) return rc;
+    *bytes = make_layout(B * C, H, W, feat_d, B).total;
+    return TL_OK;
+}
+
+int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W, int feat_d, float q,
+               float lamda, int loss_r, int B_global, void* ws, size_t ws_bytes, float* loss_out,
+               void* stream) {
+    int rc = check_shape(B, C, H, W, feat_d);
+    if (rc != TL_OK) return rc;
+    if (!pred || !truth || !ws || !loss_out) return fail(TL_ERR_ARG, "null pointer");
+    if (!(q > 0.f)) return fail(TL_ERR_ARG, "loss_q must be positive");
+    if (B_global <= 0) B_global = B;
+    const Layout L = make_layout(B * C, H, W, feat_d, B);
+    if (ws_bytes < L.total) return fail(TL_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, L.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    rc = launch_ph(pred, truth, 2, L, H, W, feat_d, ws, st);
+    if (rc != TL_OK) return rc;
+    rc = launch_sort(2, L, ws, st);
+    if (rc != TL_OK) return rc;
+
+    tl::MatchArgs m;
+    m.d1 = tl::Diagrams{reinterpret_cast<const char*>(at<tl::PairRec>(ws, L.pairs[0])) + offsetof(tl::PairRec, b),
+                        (int)sizeof(tl::PairRec), nullptr, at<int32_t>(ws, L.counts[0]), L.cap};
+    m.d2 = tl::Diagrams{reinterpret_cast<const char*>(at<tl::PairRec>(ws, L.pairs[1])) + offsetof(tl::PairRec, b),
+                        (int)sizeof(tl::PairRec), nullptr, at<int32_t>(ws, L.counts[1]), L.cap};
+    m.n_diag = L.M; m.q = q; m.loss_r = loss_r;
+    m.cost = at<double>(ws, L.cost); m.tpers = at<double>(ws, L.tpers);
+    m.match1 = at<int32_t>(ws, L.match1);
+    m.fill1 = at<tl::PairRec>(ws, L.pairs[0]);
+    fill_match_scratch(m, ws, L.v, L.minv, L.u, L.way, L.pcol, L.used, L.stride_c, L.stride_r);
+    tl::match_kernel<<<L.M < kMatchSlots ? L.M : kMatchSlots, tl::kMatchThreads, 0, st>>>(m);
+    TL_CUDA(cudaGetLastError());
+
+    tl::LossArgs la;
+    la.cost = m.cost; la.tpers = m.tpers; la.B = B; la.C = C; la.B_global = B_global; la.loss_r = loss_r;
+    la.q = q; la.lamda = lamda; la.loss_out = loss_out; la.coef = at<double>(ws, L.coef);
+    tl::loss_kernel<<<1, 256, 0, st>>>(la);
+    TL_CUDA(cudaGetLastError());
+
+    return TL_OK;
+}
+
+int tl_backward(const float* grad_loss, const void* ws, size_t ws_bytes, int B, int C, int H, int W,
+                   int feat_d, float q, float lamda, int loss_r, int B_global, float* grad_pred, void* stream) {
+    int rc = check_shape(B, C, H, W, feat_d);
+    if (rc != TL_OK) return rc;
+    if (!ws || !grad_pred) return fail(TL_ERR_ARG, "null pointer");
+    if (B_global <= 0) B_global = B;
+    const Layout L = make_layout(B * C, H, W, feat_d, B);
+    if (ws_bytes < L.total) return fail(TL_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, L.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void* w = const_cast<void*>(ws);
+    TL_CUDA(cudaMemsetAsync(grad_pred, 0, sizeof(float) * (size_t)B * C * H * W, st));
+    tl::GradArgs g;
+    g.pairs = at<tl::PairRec>(w, L.pairs[0]); g.counts = at<int32_t>(w, L.counts[0]);
+    g.coef = at<double>(w, L.coef); g.grad_loss = grad_loss;
+    g.M = L.M; g.C = C; g.cap = L.cap; g.N = H * W; g.B_global = B_global; g.loss_r = loss_r;
+    g.q = q; g.lamda = lamda; g.grad_pred = grad_pred;
+    tl::grad_kernel<<<L.M < 1184 ? L.M : 1184, 256, 0, st>>>(g);
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+int tl_persistence_pairs(const float* maps, int n_maps, int H, int W, int dim, void* ws, size_t ws_bytes,
+                         int32_t* pairs, int cap, int32_t* counts, void* stream);
+
+}  // extern "C"
+
+namespace {
+
+__global__ void export_pairs_kernel(const tl::PairRec* recs, const int32_t* cnt, int n_maps, int cap_in,
+                                    int32_t* pairs, int cap_out, int32_t* counts) {
+    for (int map = blockIdx.x; map < n_maps; map += gridDim.x) {
+        const int n = cnt[map];
+        if (threadIdx.x == 0) counts[map] = n;
+        const int lim = min(min(n, cap_in), cap_out);
+        for (int i = threadIdx.x; i < lim; i += blockDim.x) {
+            const tl::PairRec r = recs[(size_t)map * cap_in + i];
+            pairs[((size_t)map * cap_out + i) * 2] = r.cre;
+            pairs[((size_t)map * cap_out + i) * 2 + 1] = r.des;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int tl_persistence_pairs(const float* maps, int n_maps, int H, int W, int dim, void* ws, size_t ws_bytes,
+                         int32_t* pairs, int cap, int32_t* counts, void* stream) {
+    int rc = check_shape(n_maps, 1, H, W, dim);
+    if (rc != TL_OK) return rc;
+    if (!maps || !ws || !pairs || !counts || cap <= 0) return fail(TL_ERR_ARG, "null pointer or cap <= 0");
+    const Layout L = make_layout(n_maps, H, W, dim, n_maps);
+    if (ws_bytes < L.total) return fail(TL_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, L.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = launch_ph(maps, nullptr, 1, L, H, W, dim, ws, st);
+    if (rc != TL_OK) return rc;
+    rc = launch_sort(1, L, ws, st);
+    if (rc != TL_OK) return rc;
+    export_pairs_kernel<<<n_maps < 1184 ? n_maps : 1184, 256, 0, st>>>(
+        at<tl::PairRec>(ws, L.pairs[0]), at<int32_t>(ws, L.counts[0]), n_maps, L.cap, pairs, cap, counts);
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+int tl_wasserstein_workspace_bytes(int n_diag, int max_rows1, int max_rows2, size_t* bytes) {
+    if (!bytes || n_diag <= 0 || max_rows1 < 0 || max_rows2 < 0) return fail(TL_ERR_ARG, "bad arguments");
+    const size_t sc = align_up((size_t)max_rows1 + max_rows2 + 2, 32);
+    const size_t sr = align_up((size_t)(max_rows1 < max_rows2 ? max_rows1 : max_rows2) + 2, 32);
+    const int slots = n_diag < kMatchSlots ? n_diag : kMatchSlots;
+    *bytes = align_up(sizeof(double) * sc * slots) * 2 + align_up(sizeof(double) * sr * slots) +
+             align_up(sizeof(int32_t) * sc * slots) * 2 + align_up(sc * slots);
+    return TL_OK;
+}
+
+int tl_wasserstein(const float* D1, const int32_t* off1, const float* D2, const int32_t* off2, int n_diag,
+                   int max_rows1, int max_rows2, float q, void* ws, size_t ws_bytes, double* cost,
+                   int32_t* match1, void* stream) {
+    size_t need = 0;
+    int rc = tl_wasserstein_workspace_bytes(n_diag, max_rows1, max_rows2, &need);
+    if (rc != TL_OK) return rc;
+    if (!D1 || !off1 || !D2 || !off2 || !ws || !cost || !match1) return fail(TL_ERR_ARG, "null pointer");
+    if (!(q > 0.f)) return fail(TL_ERR_ARG, "q must be positive");
+    if (ws_bytes < need) return fail(TL_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, need);
+    const size_t sc = align_up((size_t)max_rows1 + max_rows2 + 2, 32);
+    const size_t sr = align_up((size_t)(max_rows1 < max_rows2 ? max_rows1 : max_rows2) + 2, 32);
+    const int slots = n_diag < kMatchSlots ? n_diag : kMatchSlots;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t a = o; o += align_up(b); return a; };
+    const size_t ov = take(sizeof(double) * sc * slots), ominv = take(sizeof(double) * sc * slots);
+    const size_t ou = take(sizeof(double) * sr * slots);
+    const size_t oway = take(sizeof(int32_t) * sc * slots), opcol = take(sizeof(int32_t) * sc * slots);
+    const size_t oused = take(sc * slots);
+    tl::MatchArgs m;
+    m.d1 = tl::Diagrams{reinterpret_cast<const char*>(D1), 8, off1, nullptr, 0};
+    m.d2 = tl::Diagrams{reinterpret_cast<const char*>(D2), 8, off2, nullptr, 0};
+    m.n_diag = n_diag; m.q = q; m.loss_r = 0; m.cost = cost; m.tpers = nullptr; m.match1 = match1; m.fill1 = nullptr;
+    fill_match_scratch(m, ws, ov, ominv, ou, oway, opcol, oused, sc, sr);
+    tl::match_kernel<<<slots, tl::kMatchThreads, 0, static_cast<cudaStream_t>(stream)>>>(m);
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+}  // extern "C"

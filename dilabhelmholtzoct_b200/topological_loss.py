@@ -1,0 +1,177 @@
+"""Drop-in replacement for the reference's topological loss.
+
+Mirrors ``topo_loss`` of ``/root/reference/octsam/models/topological_loss.py:11-96`` -- same name,
+positional order, keyword names and defaults -- as called from the SAM fine-tuning step
+(``/root/reference/octsam/models/training_utils.py:64`` and ``:375``)::
+
+    train_loss += topo_loss(torch.sigmoid(masks.float()), gt_masks.float(), 0.1, feat_d=1, interp=50)
+
+The arithmetic (cubical persistence, diagram matching, loss, gradient scatter) runs in
+``libtopoloss.so`` -- hand-written sm_100a CUDA kernels behind the C ABI of ``include/topoloss.h``.
+There is no CPU path, no PyTorch fallback and no multi-backend dispatch: tensors must live on a
+CUDA device and the library must be built, otherwise the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(B: int, C: int, H: int, W: int, feat_d: int, device) -> torch.Tensor:
+    n = ctypes.c_size_t(0)
+    _lib.check(_lib.lib().tl_workspace_bytes(B, C, H, W, feat_d, ctypes.byref(n)), "tl_workspace_bytes")
+    return torch.empty(n.value, dtype=torch.uint8, device=device)
+
+
+class _TopoLossFn(torch.autograd.Function):
+    """forward = tl_forward, backward = tl_backward (analytic backward of the reference's autograd
+    graph: MulBackward / MeanBackward / PowBackward / POT ValFunction / CdistBackward /
+    IndexBackward, i.e. what ``train_loss.backward()`` at training_utils.py:66 runs for this loss)."""
+
+    @staticmethod
+    def forward(ctx, pred, truth, lamda, feat_d, loss_q, loss_r, global_batch):
+        B, C, H, W = pred.shape
+        dev = pred.device
+        with torch.cuda.device(dev):
+            ws = _workspace(B, C, H, W, feat_d, dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            rc = _lib.lib().tl_forward(pred.data_ptr(), truth.data_ptr(), B, C, H, W, feat_d, float(loss_q),
+                                       float(lamda), int(bool(loss_r)), int(global_batch), ws.data_ptr(),
+                                       ws.numel(), loss.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "tl_forward")
+        ctx.ws = ws
+        ctx.args = (B, C, H, W, feat_d, float(loss_q), float(lamda), int(bool(loss_r)), int(global_batch))
+        ctx.pred_meta = (pred.dtype, dev)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        B, C, H, W, feat_d, q, lamda, loss_r, gb = ctx.args
+        dtype, dev = ctx.pred_meta
+        with torch.cuda.device(dev):
+            g = grad_out.to(device=dev, dtype=torch.float32).contiguous()
+            grad_pred = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+            rc = _lib.lib().tl_backward(g.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), B, C, H, W, feat_d, q,
+                                        lamda, loss_r, gb, grad_pred.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "tl_backward")
+        return grad_pred, None, None, None, None, None, None
+
+
+def _check_inputs(pred_obj, true_obj, feat_d):
+    if not (torch.is_tensor(pred_obj) and torch.is_tensor(true_obj)):
+        raise TypeError("pred_obj and true_obj must be tensors")
+    if pred_obj.shape != true_obj.shape:
+        raise ValueError(f"pred_obj {tuple(pred_obj.shape)} and true_obj {tuple(true_obj.shape)} differ in shape")
+    if pred_obj.dim() != 4:
+        raise ValueError("expected [B, C, H, W] maps (topological_loss.py:17-18 with two spatial dims)")
+    if not pred_obj.is_cuda or not true_obj.is_cuda:
+        raise ValueError("topo_loss runs on a CUDA device only: there is no CPU fallback")
+    if pred_obj.dtype != torch.float32 or true_obj.dtype != torch.float32:
+        raise ValueError("topo_loss expects float32 maps (the reference call site passes .float())")
+    if feat_d not in (0, 1):
+        # feat_d = 2 (the reference default) selects no diagram on 2-D maps and crashes in
+        # WassersteinDistance; anything outside [0, 2] crashes in batch_iter
+        raise ValueError("feat_d must be 0 or 1 for 2-D maps (the reference call site uses feat_d=1)")
+
+
+def _canonical(pred, truth) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Reproduce the nesting that ``.squeeze()`` + CubicalComplex.forward + batch_iter produce
+    (topological_loss.py:62-75): with B == 1 every channel becomes its own 'image'."""
+    B, C, H, W = pred.shape
+    if H < 2 or W < 2:
+        raise ValueError("maps must be at least 2x2 (a size-1 spatial dim is squeezed away by the reference)")
+    if B == 1 and C == 1:
+        raise ValueError("B == C == 1: the reference crashes here (batch_iter on a flat list)")
+    if B == 1:
+        pred, truth = pred.reshape(C, 1, H, W), truth.reshape(C, 1, H, W)
+    return pred.contiguous(), truth.contiguous()
+
+
+def topo_loss(pred_obj, true_obj, lamda, interp=0, feat_d=2, loss_q=2, loss_r=False):
+    """Topological loss, forward step (signature of topological_loss.py:11-12).
+
+    Args:
+        pred_obj (torch.Tensor): prediction, ``[B, C, H, W]`` float32 on a CUDA device
+        true_obj (torch.Tensor): ground truth, same shape
+        lamda (float): strength of topological regularisation; ``0.0`` returns the float ``0.0``
+        interp (int): side of the bilinear down-sample applied to both inputs (0 = none)
+        feat_d (int): homology dimension to use (0 or 1 on 2-D maps)
+        loss_q (int): exponent of the Wasserstein loss
+        loss_r (bool): add the total-persistence regulariser of the prediction
+
+    Returns:
+        0-d float32 tensor on ``pred_obj.device`` attached to autograd.
+    """
+    if lamda == 0.0:  # topological_loss.py:30-31
+        return 0.0
+    _check_inputs(pred_obj, true_obj, feat_d)
+    if interp != 0:  # topological_loss.py:33-46
+        size = (interp,) * 2
+        pred_obj = F.interpolate(pred_obj, size=size, mode="bilinear", align_corners=True)
+        true_obj = F.interpolate(true_obj, size=size, mode="bilinear", align_corners=True)
+    pred, truth = _canonical(pred_obj, true_obj.detach())
+    return _TopoLossFn.apply(pred, truth, lamda, feat_d, loss_q, loss_r, 0)
+
+
+# ---------------------------------------------------------------- inner boundaries (parity tests)
+
+def persistence_pairs(maps: torch.Tensor, dim: int) -> List[torch.Tensor]:
+    """CubicalComplex(dim=2, superlevel=False) on ``[..., H, W]`` maps: per map an int32 ``[K, 2]``
+    tensor of (creator, destroyer) flat pixel indices in gudhi's emission order; for ``dim == 0`` the
+    essential class, paired with ``argmax``, comes last (torch_topological
+    CubicalComplex._extract_generators_and_diagrams; reference call topological_loss.py:62)."""
+    if not maps.is_cuda or maps.dtype != torch.float32:
+        raise ValueError("persistence_pairs expects float32 CUDA maps")
+    H, W = maps.shape[-2:]
+    flat = maps.reshape(-1, H, W).contiguous()
+    n = flat.shape[0]
+    L = _lib.lib()
+    cap = L.tl_max_pairs(H, W, dim)
+    if cap < 0:
+        _lib.check(cap, "tl_max_pairs")
+    dev = maps.device
+    with torch.cuda.device(dev):
+        ws = _workspace(n, 1, H, W, dim, dev)
+        pairs = torch.empty((n, cap, 2), dtype=torch.int32, device=dev)
+        counts = torch.empty((n,), dtype=torch.int32, device=dev)
+        rc = L.tl_persistence_pairs(flat.data_ptr(), n, H, W, dim, ws.data_ptr(), ws.numel(), pairs.data_ptr(),
+                                    cap, counts.data_ptr(), _stream_ptr(dev))
+    _lib.check(rc, "tl_persistence_pairs")
+    cnt = counts.cpu().tolist()
+    return [pairs[i, :c].clone() for i, c in enumerate(cnt)]
+
+
+def wasserstein_cost(D1: Sequence[torch.Tensor], D2: Sequence[torch.Tensor], q: float = 2.0):
+    """Per diagram pair: the ``ot.emd2`` value WassersteinDistance(q) sums (before the 1/q root,
+    topological_loss.py:78-82) and, for every row of D1[k], the matched row of D2[k] or -1."""
+    assert len(D1) == len(D2) and len(D1) > 0
+    dev = D1[0].device
+    if dev.type != "cuda":
+        raise ValueError("wasserstein_cost expects CUDA tensors")
+    n1 = [int(d.shape[0]) for d in D1]
+    n2 = [int(d.shape[0]) for d in D2]
+    off1 = torch.tensor([0] + list(torch.tensor(n1).cumsum(0).tolist()), dtype=torch.int32, device=dev)
+    off2 = torch.tensor([0] + list(torch.tensor(n2).cumsum(0).tolist()), dtype=torch.int32, device=dev)
+    A = torch.cat([d.reshape(-1, 2).float() for d in D1] + [torch.zeros((1, 2), device=dev)]).contiguous()
+    Bm = torch.cat([d.reshape(-1, 2).float() for d in D2] + [torch.zeros((1, 2), device=dev)]).contiguous()
+    L = _lib.lib()
+    nb = ctypes.c_size_t(0)
+    _lib.check(L.tl_wasserstein_workspace_bytes(len(D1), max(n1), max(n2), ctypes.byref(nb)), "tl_wasserstein_workspace_bytes")
+    with torch.cuda.device(dev):
+        ws = torch.empty(max(nb.value, 1), dtype=torch.uint8, device=dev)
+        cost = torch.empty(len(D1), dtype=torch.float64, device=dev)
+        match = torch.full((sum(n1) + 1,), -2, dtype=torch.int32, device=dev)
+        rc = L.tl_wasserstein(A.data_ptr(), off1.data_ptr(), Bm.data_ptr(), off2.data_ptr(), len(D1), max(n1), max(n2),
+                              float(q), ws.data_ptr(), ws.numel(), cost.data_ptr(), match.data_ptr(), _stream_ptr(dev))
+    _lib.check(rc, "tl_wasserstein")
+    o = off1.cpu().tolist()
+    return cost, [match[o[k]:o[k + 1]] for k in range(len(D1))]

@@ -1,0 +1,211 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+Bit-exact for persistence pairs / critical pixels; loss and gradient within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.kats import KATS
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5  # north_star: loss values and gradients agree within 1e-5 relative in fp32
+
+
+def _gpu_pairs(maps, dim):
+    import dilabhelmholtzoct_b200 as tlb
+    out = tlb.persistence_pairs(torch.as_tensor(maps, dtype=torch.float32, device="cuda"), dim)
+    return [p.cpu().numpy() for p in out]
+
+
+def _assert_same_pairs(maps, dim):
+    got = _gpu_pairs(maps, dim)
+    for k, f in enumerate(maps):
+        want = oracle.cubical_pairs(f, dim)
+        assert got[k].shape == want.shape, (k, dim, got[k].shape, want.shape)
+        assert np.array_equal(got[k], want), (k, dim)
+
+
+@pytest.mark.parametrize("name", sorted(KATS))
+def test_kats(name):
+    img, h0, h1, ess = KATS[name]
+    f = np.array(img, dtype=np.float32)
+    if f.shape[0] != f.shape[1]:
+        pytest.skip("non-square maps are rejected by the CUDA path")
+    g0 = _gpu_pairs(f[None], 0)[0]
+    g1 = _gpu_pairs(f[None], 1)[0]
+    assert sorted(map(tuple, g0[:-1].tolist())) == sorted(h0)
+    assert tuple(g0[-1].tolist()) == ess
+    assert sorted(map(tuple, g1.tolist())) == sorted(h1)
+
+
+@pytest.mark.parametrize("dim", [0, 1])
+@pytest.mark.parametrize("size", [2, 3, 5, 8, 17, 32, 50, 64])
+def test_pairs_random(dim, size):
+    rng = np.random.default_rng(100 + size)
+    maps = rng.random((12, size, size)).astype(np.float32)
+    _assert_same_pairs(maps, dim)
+
+
+@pytest.mark.parametrize("dim", [0, 1])
+@pytest.mark.parametrize("levels", [2, 4, 32, 1024])
+def test_pairs_ties(dim, levels):
+    """Tie-heavy maps: critical-pixel indices depend on gudhi's (value, dim, position) cell order."""
+    rng = np.random.default_rng(7 + levels)
+    maps = (rng.integers(0, levels, (16, 24, 24)) / levels).astype(np.float32)
+    maps = np.concatenate([maps, np.zeros((1, 24, 24), np.float32), np.ones((1, 24, 24), np.float32)])
+    _assert_same_pairs(maps, dim)
+
+
+@pytest.mark.parametrize("dim", [0, 1])
+def test_pairs_256_synthetic(dim):
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(1, 256, 256, seed=4321)
+    maps = torch.cat([pred[0], truth[0]]).numpy()
+    _assert_same_pairs(maps, dim)
+
+
+@pytest.mark.parametrize("dim", [0, 1])
+def test_pairs_signed_and_negative_zero(dim):
+    rng = np.random.default_rng(3)
+    maps = (rng.integers(-3, 4, (8, 16, 16))).astype(np.float32)
+    maps[maps == 0] = np.where(rng.random((maps == 0).sum()) < 0.5, -0.0, 0.0)
+    _assert_same_pairs(maps, dim)
+
+
+def test_pairs_repeatable():
+    rng = np.random.default_rng(11)
+    maps = rng.random((6, 96, 96)).astype(np.float32)
+    a = _gpu_pairs(maps, 1)
+    for _ in range(3):
+        b = _gpu_pairs(maps, 1)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("q", [1.0, 2.0, 3.0])
+def test_wasserstein_vs_oracle(q):
+    import dilabhelmholtzoct_b200 as tlb
+    rng = np.random.default_rng(int(q) * 13)
+    D1, D2 = [], []
+    for t in range(40):
+        n, m = int(rng.integers(0, 60)), int(rng.integers(0, 12))
+        if t % 7 == 0:
+            n, m = m, n
+        b = rng.random(n).astype(np.float32)
+        D1.append(np.stack([b, b + rng.random(n).astype(np.float32)], 1).reshape(-1, 2))
+        b = rng.random(m).astype(np.float32)
+        d2 = np.stack([b, b + rng.random(m).astype(np.float32)], 1).reshape(-1, 2)
+        if t % 5 == 0 and m:
+            d2[:] = np.array([0.0, 1.0], np.float32)  # binary ground truth: identical points
+        D2.append(d2)
+    cost, match = tlb.wasserstein_cost([torch.tensor(d, device="cuda") for d in D1],
+                                       [torch.tensor(d, device="cuda") for d in D2], q)
+    cost = cost.cpu().numpy()
+    for k in range(len(D1)):
+        want, _ = oracle.wasserstein(D1[k], D2[k], q)
+        assert abs(cost[k] - want) <= 1e-9 + 1e-7 * abs(want), (k, cost[k], want)
+        mk = match[k].cpu().numpy()
+        used = mk[mk >= 0]
+        assert len(set(used.tolist())) == len(used) and (used < len(D2[k])).all()
+
+
+def _loss_and_grad(pred, truth, lamda, **kw):
+    import dilabhelmholtzoct_b200 as tlb
+    p = pred.clone().cuda().requires_grad_(True)
+    loss = tlb.topo_loss(p, truth.cuda(), lamda, **kw)
+    loss.backward()
+    return float(loss), p.grad.cpu().numpy()
+
+
+def _check_loss(pred, truth, lamda, feat_d, q=2, loss_r=False):
+    loss, grad = _loss_and_grad(pred, truth, lamda, feat_d=feat_d, loss_q=q, loss_r=loss_r)
+    want, wgrad, _ = oracle.topo_loss(pred.numpy(), truth.numpy(), lamda, feat_d=feat_d, loss_q=q, loss_r=loss_r)
+    assert abs(loss - want) <= REL * abs(want) + 1e-12, (loss, want)
+    scale = np.abs(wgrad).max()
+    assert np.array_equal(grad != 0, wgrad != 0), "critical pixels differ"
+    assert np.abs(grad - wgrad).max() <= REL * scale + 1e-12, (np.abs(grad - wgrad).max(), scale)
+
+
+@pytest.mark.parametrize("feat_d", [0, 1])
+@pytest.mark.parametrize("q", [1, 2])
+def test_loss_small(feat_d, q):
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(3, 48, 48, seed=77, n_classes=5)
+    _check_loss(pred, truth, 0.1, feat_d, q=q)
+
+
+def test_loss_regulariser():
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(2, 40, 40, seed=78, n_classes=4)
+    _check_loss(pred, truth, 0.25, 1, q=2, loss_r=True)
+
+
+def test_loss_nonbinary_truth():
+    """interp-style ground truth (fractional values -> several truth points per map)."""
+    rng = torch.Generator().manual_seed(5)
+    pred = torch.rand((2, 3, 50, 50), generator=rng)
+    truth = torch.nn.functional.avg_pool2d(torch.rand((2, 3, 100, 100), generator=rng), 2)
+    _check_loss(pred, truth, 0.1, 1)
+    _check_loss(pred, truth, 0.1, 0)
+
+
+def test_loss_256x14():
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(2, 256, 256, seed=1234)
+    _check_loss(pred, truth, 0.1, 1)
+
+
+def test_interp_and_upstream_grad():
+    import dilabhelmholtzoct_b200 as tlb
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(2, 96, 96, seed=9, n_classes=4)
+    logits = torch.logit(pred.clamp(1e-4, 1 - 1e-4)).cuda().requires_grad_(True)
+    loss = 3.0 * tlb.topo_loss(torch.sigmoid(logits), truth.cuda(), 0.1, feat_d=1, interp=50)
+    loss.backward()
+    # oracle on the resampled maps, chained through interpolate + sigmoid by autograd
+    lg = logits.detach().cpu().requires_grad_(True)
+    ps = torch.nn.functional.interpolate(torch.sigmoid(lg), size=(50, 50), mode="bilinear", align_corners=True)
+    ts = torch.nn.functional.interpolate(truth, size=(50, 50), mode="bilinear", align_corners=True)
+    want, wgrad, _ = oracle.topo_loss(ps.detach().numpy(), ts.numpy(), 0.1, feat_d=1)
+    ps.backward(torch.tensor(wgrad) * 3.0)
+    assert abs(float(loss) - 3.0 * want) <= REL * abs(3.0 * want)
+    g, w = logits.grad.cpu().numpy(), lg.grad.numpy()
+    assert np.abs(g - w).max() <= 1e-4 * np.abs(w).max()
+
+
+def test_squeeze_quirk_batch_of_one():
+    """B == 1: .squeeze() makes every channel its own image."""
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(1, 32, 32, seed=3, n_classes=4)
+    loss, grad = _loss_and_grad(pred, truth, 0.1, feat_d=1)
+    want, wgrad, _ = oracle.topo_loss(pred.permute(1, 0, 2, 3).contiguous().numpy(),
+                                      truth.permute(1, 0, 2, 3).contiguous().numpy(), 0.1, feat_d=1)
+    assert abs(loss - want) <= REL * abs(want)
+    assert np.abs(grad - wgrad.transpose(1, 0, 2, 3)).max() <= REL * np.abs(wgrad).max()
+
+
+def test_errors_and_early_out():
+    import dilabhelmholtzoct_b200 as tlb
+    x = torch.rand((2, 2, 8, 8), device="cuda")
+    assert tlb.topo_loss(x, x, 0.0) == 0.0
+    with pytest.raises(ValueError):
+        tlb.topo_loss(x, x, 0.1)  # default feat_d=2 is invalid on 2-D maps
+    with pytest.raises(ValueError):
+        tlb.topo_loss(x.cpu(), x.cpu(), 0.1, feat_d=1)  # no CPU fallback
+    with pytest.raises(ValueError):
+        tlb.topo_loss(torch.rand((2, 2, 8, 9), device="cuda"), torch.rand((2, 2, 8, 9), device="cuda"), 0.1, feat_d=1)
+    with pytest.raises(ValueError):
+        tlb.topo_loss(x[:1, :1], x[:1, :1], 0.1, feat_d=1)
+
+
+def test_zero_cost_gives_nan_grad():
+    """S_b == 0 -> pow(1/q) backward is inf * 0 = NaN in the reference's autograd."""
+    import dilabhelmholtzoct_b200 as tlb
+    rng = np.random.default_rng(0)
+    f = torch.tensor(rng.random((2, 2, 12, 12)).astype(np.float32), device="cuda")
+    p = f.clone().requires_grad_(True)
+    loss = tlb.topo_loss(p, f, 0.1, feat_d=1)
+    loss.backward()
+    assert float(loss) == 0.0
+    g = p.grad
+    assert torch.isnan(g).any() and not torch.isnan(g).all()
