@@ -43,9 +43,13 @@ struct Ph {
 
     __device__ __forceinline__ int find0(int x) const {
         for (;;) {
-            uint64_t t = ld_cg_u64(T + x);
+            const uint64_t t = ld_cg_u64(T + x);
             if ((uint32_t)(t >> 32) != kCodeL0) return x;
-            x = (int)(uint32_t)t;
+            const int p = (int)(uint32_t)t;
+            const uint64_t tp = ld_cg_u64(T + p);
+            if ((uint32_t)(tp >> 32) != kCodeL0) return p;
+            T[x] = tp;  // path halving: a level-0 entry only ever holds an ancestor
+            x = (int)(uint32_t)tp;
         }
     }
 
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
             PairRec rec;
             uint64_t sk = 0;
             if (x < NN) {
-                const uint64_t t = T[x];
+                const uint64_t t = ld_cg_u64(T + x);
                 const uint32_t code = (uint32_t)(t >> 32);
                 if (code != kCodeL0 && code != kCodeRoot) {
                     const uint32_t pos = code - 1;

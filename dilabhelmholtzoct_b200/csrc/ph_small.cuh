@@ -1,0 +1,409 @@
+// Shared-memory persistence kernel for maps with at most 65535 nodes (+ OUTSIDE): 50x50 .. 256x256.
+// One CTA per (image, class) map; same algorithm as ph_kernel.cuh (elder-linked union-find, then a
+// lock-free triplet merge tree), but every latency-critical structure lives in shared memory:
+//
+//   phase A  level-0 union-find on 16-bit parents        par[65536]            (128 KB)
+//   census   basin roots get dense ids in raster order   root mask             (  8 KB)
+//            -> per-pixel basin id B[] (global, streamed), root pixel / root value per basin
+//   phase B  triplet table over BASINS only, 16-byte self-contained entries
+//            {edge key 64, elder target 32, own root value 32}, updated with ATOMS.CAS.128
+//            (reuses phase A's shared memory; K <= ~14.5k basins fit, else global fallback)
+//   emit     one pair per basin with a recorded edge and positive persistence
+//
+// OUTSIDE (H1 only) is node 0xFFFF.  When H*W == 65536 that index is also the last pixel, which is
+// sound: the bottom-right pixel's earliest edge is always its bottom boundary edge (largest bitmap
+// position among its edges, value = its own), so it merges into OUTSIDE at zero persistence first.
+#pragma once
+#include "ph_kernel.cuh"
+
+namespace tl {
+
+constexpr int kSmallMaxNodes = 65535;
+constexpr uint32_t kOut16 = 0xFFFFu;
+constexpr uint64_t kRootKey = ~0ull;
+constexpr int kParBytes = 65536 * 2;
+constexpr int kMaskBytes = 65536 / 8;
+constexpr int kSmallSmemBytes = 226 * 1024;  // dynamic shared memory of ph_small_kernel
+
+struct __align__(16) TEntry {
+    uint64_t ekey;    // key of the edge at which this basin dies (kRootKey: still alive)
+    uint32_t target;  // an elder basin it merged into (self while alive)
+    uint32_t zval;    // ordered value of this basin's eldest node (immutable)
+};
+
+template <bool SM>
+__device__ __forceinline__ TEntry t_load(const TEntry* p) {
+    uint32_t a, b, c, d;
+    if (SM) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
+        asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(sa) : "memory");
+    } else {
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+    }
+    TEntry e;
+    e.ekey = (uint64_t)a | ((uint64_t)b << 32);
+    e.target = c;
+    e.zval = d;
+    return e;
+}
+
+template <bool SM>
+__device__ __forceinline__ bool t_cas(TEntry* p, const TEntry& expect, const TEntry& want) {
+    const uint64_t e_hi = (uint64_t)expect.target | ((uint64_t)expect.zval << 32);
+    const uint64_t d_hi = (uint64_t)want.target | ((uint64_t)want.zval << 32);
+    uint64_t o_lo, o_hi;
+    if (SM) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
+        asm volatile(
+            "{\n .reg .b128 e, d, o;\n mov.b128 e, {%3, %4};\n mov.b128 d, {%5, %6};\n"
+            " atom.shared.cas.b128 o, [%2], e, d;\n mov.b128 {%0, %1}, o;\n}\n"
+            : "=l"(o_lo), "=l"(o_hi) : "r"(sa), "l"(expect.ekey), "l"(e_hi), "l"(want.ekey), "l"(d_hi) : "memory");
+    } else {
+        asm volatile(
+            "{\n .reg .b128 e, d, o;\n mov.b128 e, {%3, %4};\n mov.b128 d, {%5, %6};\n"
+            " atom.global.cas.b128 o, [%2], e, d;\n mov.b128 {%0, %1}, o;\n}\n"
+            : "=l"(o_lo), "=l"(o_hi) : "l"(p), "l"(expect.ekey), "l"(e_hi), "l"(want.ekey), "l"(d_hi) : "memory");
+    }
+    return o_lo == expect.ekey && o_hi == e_hi;
+}
+
+// elder test between basins (ids are dense in raster order of their root node)
+template <int DIM>
+__device__ __forceinline__ bool basin_elder(uint32_t x, uint32_t zx, uint32_t y, uint32_t zy) {
+    if (DIM == 1) {
+        if (x == 0u) return true;   // OUTSIDE
+        if (y == 0u) return false;
+        return zx != zy ? zx < zy : x > y;  // complemented values; larger raster index = elder
+    }
+    return zx != zy ? zx < zy : x < y;
+}
+
+template <bool SM>
+__device__ __forceinline__ uint32_t rep2(const TEntry* T, uint32_t x, uint64_t skey, TEntry& entry) {
+    for (;;) {
+        const TEntry e = t_load<SM>(T + x);
+        if (e.ekey > skey) { entry = e; return x; }
+        x = e.target;
+    }
+}
+
+template <int DIM, bool SM>
+__device__ void merge2(TEntry* T, uint32_t a, uint32_t b, uint64_t skey) {
+    for (;;) {
+        TEntry ea, eb;
+        uint32_t x = rep2<SM>(T, a, skey, ea), y = rep2<SM>(T, b, skey, eb);
+        if (x == y) return;
+        if (basin_elder<DIM>(y, eb.zval, x, ea.zval)) { uint32_t t = x; x = y; y = t; eb = ea; }
+        TEntry want;
+        want.ekey = skey; want.target = x; want.zval = eb.zval;
+        if (t_cas<SM>(T + y, eb, want)) {
+            if (eb.ekey == kRootKey) return;
+            a = x; b = eb.target; skey = eb.ekey;  // re-assert y's former connection for x
+        } else {
+            a = x; b = y;
+        }
+    }
+}
+
+struct PhSmallArgs {
+    PhArgs base;
+    uint16_t* Bg;        // [grid][b_stride] basin id per node
+    uint32_t* rootpix;   // [grid][k_stride] root node of each basin
+    uint32_t* zval;      // [grid][k_stride]
+    TEntry* T2g;         // [grid][k_stride] fallback triplet table
+    size_t b_stride, k_stride;
+    unsigned long long* prof;  // optional [8] phase cycle counters
+};
+
+template <int DIM>
+struct SmallCtx {
+    Geo<DIM> g;
+    uint16_t* par;
+    __device__ __forceinline__ SmallCtx(const float* f, int H, int W, uint16_t* par_) : g(f, H, W), par(par_) {}
+
+    __device__ __forceinline__ uint32_t find(uint32_t x) const {
+        volatile uint16_t* p = par;
+        uint32_t px = p[x];
+        while (px != x) {
+            const uint32_t gp = p[px];
+            if (gp != px) p[x] = (uint16_t)gp;  // path halving; non-root entries only ever hold ancestors
+            x = px; px = gp;
+        }
+        return x;
+    }
+    __device__ __forceinline__ bool elder(uint32_t x, uint32_t y) const {
+        if (DIM == 1) {
+            if (x == kOut16) return true;
+            if (y == kOut16) return false;
+        }
+        return g.nkey((int)x) < g.nkey((int)y);
+    }
+    __device__ void union0(uint32_t a, uint32_t b) {
+        for (;;) {
+            uint32_t ra = find(a), rb = find(b);
+            if (ra == rb) return;
+            if (elder(rb, ra)) { uint32_t t = ra; ra = rb; rb = t; }
+            const unsigned short old = atomicCAS(reinterpret_cast<unsigned short*>(par + rb), (unsigned short)rb, (unsigned short)ra);
+            if (old == (unsigned short)rb) return;
+            a = ra; b = rb;
+        }
+    }
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned int s_job;
+    __shared__ int s_count, s_K;
+    __shared__ unsigned long long s_argmax;
+    __shared__ int s_wcnt[kPhThreads / 32];
+    const PhArgs& A = S.base;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int H = A.H, W = A.W, N = H * W;
+    uint16_t* par = reinterpret_cast<uint16_t*>(smem);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(smem + kParBytes);
+    TEntry* Ts = reinterpret_cast<TEntry*>(smem);
+    const int t_cap_smem = kSmallSmemBytes / (int)sizeof(TEntry);
+    uint16_t* Bg = S.Bg + (size_t)blockIdx.x * S.b_stride;
+    uint32_t* rootpix = S.rootpix + (size_t)blockIdx.x * S.k_stride;
+    uint32_t* zvalg = S.zval + (size_t)blockIdx.x * S.k_stride;
+    const unsigned int n_jobs = (unsigned)A.n_sets * (unsigned)A.n_maps;
+    long long t0 = 0;
+#define TL_PROF(slot)                                                        \
+    do {                                                                     \
+        if (S.prof && tid == 0) { long long t1 = clock64(); atomicAdd(S.prof + (slot), (unsigned long long)(t1 - t0)); t0 = t1; } \
+    } while (0)
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_job = atomicAdd(A.job_counter, 1u); s_count = 0; s_argmax = 0ull; }
+        __syncthreads();
+        const unsigned int job = s_job;
+        if (job >= n_jobs) break;
+        if (S.prof && tid == 0) t0 = clock64();
+        const int set = (int)(job % (unsigned)A.n_sets), map = (int)(job / (unsigned)A.n_sets);
+        SmallCtx<DIM> cx(A.maps[set] + (size_t)map * N, H, W, par);
+        const Geo<DIM>& g = cx.g;
+        const int NN = g.NN, GW = g.GW, VW = g.VW;
+        const int n_real = DIM == 1 ? N : NN;  // nodes that own a slot besides OUTSIDE
+
+        // ---- phase 0
+        for (int x = tid; x < 65536; x += nt) par[x] = (uint16_t)x;
+        if (DIM == 0) {
+            unsigned long long best = 0ull;
+            for (int p = tid; p < N; p += nt) {
+                unsigned long long k = ((unsigned long long)mono32(__ldg(g.f + p)) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)p);
+                best = k > best ? k : best;
+            }
+            atomicMax(&s_argmax, best);
+        }
+        __syncthreads();
+        TL_PROF(0);
+
+        // ---- phase 1: level-0 union-find in shared memory
+        const bool alias = DIM == 1 && N == 65536;  // last pixel == OUTSIDE
+        for (int x = tid; x < n_real; x += nt) {
+            if (alias && x == N - 1) continue;
+            uint64_t best = ~0ull;
+            int other = -1;
+            if (DIM == 1) {
+                const int r = x / W, c = x - r * W;
+                const float fp = g.px(r, c);
+                {
+                    float v = r == 0 ? fp : fminf(fp, g.px(r - 1, c));
+                    uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 1 + (2 * r) * GW));
+                    if (k < best) { best = k; other = r == 0 ? (int)kOut16 : x - W; }
+                }
+                {
+                    float v = r == H - 1 ? fp : fminf(fp, g.px(r + 1, c));
+                    uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 1 + (2 * r + 2) * GW));
+                    if (k < best) { best = k; other = r == H - 1 ? (int)kOut16 : x + W; }
+                }
+                {
+                    float v = c == 0 ? fp : fminf(fp, g.px(r, c - 1));
+                    uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + (2 * r + 1) * GW));
+                    if (k < best) { best = k; other = c == 0 ? (int)kOut16 : x - 1; }
+                }
+                {
+                    float v = c == W - 1 ? fp : fminf(fp, g.px(r, c + 1));
+                    uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 2 + (2 * r + 1) * GW));
+                    if (k < best) { best = k; other = c == W - 1 ? (int)kOut16 : x + 1; }
+                }
+                if ((uint32_t)(best >> 32) != (uint32_t)(g.make_ekey(fp, 0u) >> 32)) other = -1;  // strict local max
+                if (alias && other == N - 1) other = (int)kOut16;
+            } else {
+                const int i = x / VW, j = x - i * VW;
+                if (i > 0) {
+                    uint64_t k = g.make_ekey(g.vedge_val(i - 1, j), (uint32_t)(2 * j + (2 * i - 1) * GW));
+                    if (k < best) { best = k; other = x - VW; }
+                }
+                if (i < H) {
+                    uint64_t k = g.make_ekey(g.vedge_val(i, j), (uint32_t)(2 * j + (2 * i + 1) * GW));
+                    if (k < best) { best = k; other = x + VW; }
+                }
+                if (j > 0) {
+                    uint64_t k = g.make_ekey(g.hedge_val(i, j - 1), (uint32_t)(2 * j - 1 + (2 * i) * GW));
+                    if (k < best) { best = k; other = x - 1; }
+                }
+                if (j < W) {
+                    uint64_t k = g.make_ekey(g.hedge_val(i, j), (uint32_t)(2 * j + 1 + (2 * i) * GW));
+                    if (k < best) { best = k; other = x + 1; }
+                }
+            }
+            if (other >= 0) cx.union0((uint32_t)x, (uint32_t)other);
+        }
+        __syncthreads();
+        TL_PROF(1);
+        for (int x = tid; x < n_real; x += nt) {
+            const uint32_t r = cx.find((uint32_t)x);
+            par[x] = (uint16_t)r;
+        }
+        __syncthreads();
+        TL_PROF(2);
+
+        // ---- census: dense basin ids in raster order of the roots
+        const int chunk = (((n_real + 31) / 32) + 31) & ~31;
+        const int beg = min(n_real, warp * chunk), end = min(n_real, beg + chunk);
+        {
+            int cnt = 0;
+            for (int i0 = beg; i0 < end; i0 += 32) {
+                const int i = i0 + lane;
+                const bool root = i < end && par[i] == (uint16_t)i && !(DIM == 1 && (uint32_t)i == kOut16);
+                cnt += __popc(__ballot_sync(0xFFFFFFFFu, root));
+            }
+            if (lane == 0) s_wcnt[warp] = cnt;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int v = s_wcnt[lane];
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+            s_wcnt[lane] = incl - v;
+            if (lane == 31) s_K = incl;
+        }
+        __syncthreads();
+        const int K = s_K;  // basins 1..K (0 = OUTSIDE for H1, unused for H0)
+        {
+            int run = s_wcnt[warp];
+            for (int i0 = beg; i0 < end; i0 += 32) {
+                const int i = i0 + lane;
+                const bool root = i < end && par[i] == (uint16_t)i && !(DIM == 1 && (uint32_t)i == kOut16);
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, root);
+                if (lane == 0) mask[i0 >> 5] = bal;
+                if (root) {
+                    const int cid = 1 + run + __popc(bal & lanemask_lt());
+                    rootpix[cid] = (uint32_t)i;
+                    zvalg[cid] = (uint32_t)(g.nkey(i) >> 32);
+                    par[i] = (uint16_t)cid;
+                }
+                run += __popc(bal);
+            }
+        }
+        __syncthreads();
+        for (int x = tid; x < n_real; x += nt) {
+            uint32_t b;
+            if ((mask[x >> 5] >> (x & 31)) & 1u) b = par[x];
+            else {
+                const uint32_t r = par[x];
+                b = (DIM == 1 && r == kOut16) ? 0u : par[r];
+            }
+            Bg[x] = (uint16_t)b;
+        }
+        __syncthreads();
+        TL_PROF(3);
+
+        // ---- phase B: triplet merge tree over basins
+        const bool t_in_smem = K + 1 <= t_cap_smem;
+        TEntry* T = t_in_smem ? Ts : S.T2g + (size_t)blockIdx.x * S.k_stride;
+        for (int c = tid; c <= K; c += nt) {
+            TEntry e;
+            e.ekey = kRootKey; e.target = (uint32_t)c; e.zval = c ? zvalg[c] : 0u;
+            T[c] = e;
+        }
+        __syncthreads();
+        const int n_vedges = H * (W + 1), n_hedges = (H + 1) * W;
+        for (int e = tid; e < n_vedges + n_hedges; e += nt) {
+            int a, b;
+            uint32_t pos;
+            int ei, ej;
+            const bool is_v = e < n_vedges;
+            if (is_v) {
+                ei = e / (W + 1); ej = e - ei * (W + 1);
+                pos = (uint32_t)(2 * ej + (2 * ei + 1) * GW);
+                if (DIM == 1) { a = ej == 0 ? -1 : ei * W + ej - 1; b = ej == W ? -1 : ei * W + ej; }
+                else { a = ei * VW + ej; b = a + VW; }
+            } else {
+                const int e2 = e - n_vedges;
+                ei = e2 / W; ej = e2 - ei * W;
+                pos = (uint32_t)(2 * ej + 1 + (2 * ei) * GW);
+                if (DIM == 1) { a = ei == 0 ? -1 : (ei - 1) * W + ej; b = ei == H ? -1 : ei * W + ej; }
+                else { a = ei * VW + ej; b = a + 1; }
+            }
+            const uint32_t la = a < 0 ? 0u : Bg[a], lb = b < 0 ? 0u : Bg[b];
+            if (la == lb) continue;
+            const float val = is_v ? g.vedge_val(ei, ej) : g.hedge_val(ei, ej);
+            const uint64_t skey = g.make_ekey(val, pos);
+            if (t_in_smem) merge2<DIM, true>(T, la, lb, skey);
+            else merge2<DIM, false>(T, la, lb, skey);
+        }
+        __syncthreads();
+        TL_PROF(4);
+
+        // ---- emit
+        PairRec* out = A.pairs[set] + (size_t)map * A.cap;
+        uint64_t* skeys = A.skeys[set] ? A.skeys[set] + (size_t)map * A.cap : nullptr;
+        for (int c0 = 1; c0 <= K; c0 += nt) {
+            const int c = c0 + tid;
+            bool emit = false;
+            PairRec rec;
+            uint64_t sk = 0;
+            if (c <= K) {
+                const TEntry e = t_in_smem ? t_load<true>(T + c) : t_load<false>(T + c);
+                const int x = (int)rootpix[c];
+                if (e.ekey != kRootKey) {
+                    if ((uint32_t)(e.ekey >> 32) != e.zval) {
+                        emit = true;
+                        if (DIM == 1) {
+                            rec.cre = g.edge_top((uint32_t)(~e.ekey));
+                            rec.des = x;
+                            sk = ((uint64_t)(~e.zval) << 32) | (uint32_t)x;  // death cell = square x
+                        } else {
+                            g.vertex_val(x / VW, x % VW, &rec.cre);
+                            rec.des = g.edge_top((uint32_t)e.ekey);
+                            sk = e.ekey;  // death cell = edge
+                        }
+                    }
+                } else if (DIM == 0) {  // essential class
+                    emit = true;
+                    g.vertex_val(x / VW, x % VW, &rec.cre);
+                    rec.des = (int)(0xFFFFFFFFu - (uint32_t)s_argmax);
+                    sk = ~0ull;
+                }
+            }
+            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, emit);
+            if (ballot) {
+                int base = 0;
+                const int leader = __ffs(ballot) - 1;
+                if (lane == leader) base = atomicAdd(&s_count, __popc(ballot));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (emit) {
+                    const int slot = base + __popc(ballot & lanemask_lt());
+                    if (slot < A.cap) {
+                        rec.b = __ldg(g.f + rec.cre);
+                        rec.d = __ldg(g.f + rec.des);
+                        rec.tb = rec.td = __int_as_float(0x7FC00000);
+                        out[slot] = rec;
+                        if (skeys) skeys[slot] = sk;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) A.counts[set][map] = s_count;
+        TL_PROF(5);
+    }
+#undef TL_PROF
+}
+
+}  // namespace tl

@@ -6,10 +6,12 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "match_kernel.cuh"
 #include "ph_kernel.cuh"
+#include "ph_small.cuh"
 #include "seg_sort.cuh"
 
 namespace {
@@ -46,6 +48,8 @@ struct Layout {
     int M, cap, n_nodes;
     size_t counter, counts[2], cost, tpers, coef, pairs[2], skeys[2], match1;
     size_t T, t_stride;
+    int small;  // 1: shared-memory persistence kernel (<= 65535 nodes)
+    size_t Bg, b_stride, rootpix, zval, T2g, k_stride;
     size_t key_tmp, idx_a, idx_b, rec_tmp;
     size_t v, minv, u, way, pcol, used, stride_c, stride_r;
     size_t total;
@@ -68,8 +72,18 @@ Layout make_layout(int M, int H, int W, int dim, int B) {
     for (int s = 0; s < 2; ++s) L.pairs[s] = take(sizeof(tl::PairRec) * (size_t)M * L.cap);
     for (int s = 0; s < 2; ++s) L.skeys[s] = take(sizeof(uint64_t) * (size_t)M * L.cap);
     L.match1 = take(sizeof(int32_t) * (size_t)M * L.cap);
-    L.t_stride = align_up(sizeof(uint64_t) * (size_t)L.n_nodes) / sizeof(uint64_t);
-    L.T = take(sizeof(uint64_t) * L.t_stride * kPhSlots);
+    L.small = dim == 1 ? ((long long)H * W <= 65536) : (L.n_nodes <= tl::kSmallMaxNodes);
+    if (L.small) {
+        L.b_stride = align_up(sizeof(uint16_t) * (size_t)L.n_nodes) / sizeof(uint16_t);
+        L.k_stride = align_up((size_t)L.cap + 2, 64);
+        L.Bg = take(sizeof(uint16_t) * L.b_stride * kPhSlots);
+        L.rootpix = take(sizeof(uint32_t) * L.k_stride * kPhSlots);
+        L.zval = take(sizeof(uint32_t) * L.k_stride * kPhSlots);
+        L.T2g = take(sizeof(tl::TEntry) * L.k_stride * kPhSlots);
+    } else {
+        L.t_stride = align_up(sizeof(uint64_t) * (size_t)L.n_nodes) / sizeof(uint64_t);
+        L.T = take(sizeof(uint64_t) * L.t_stride * kPhSlots);
+    }
     L.key_tmp = take(sizeof(uint64_t) * (size_t)L.cap * kSortSlots);
     L.idx_a = take(sizeof(uint32_t) * (size_t)L.cap * kSortSlots);
     L.idx_b = take(sizeof(uint32_t) * (size_t)L.cap * kSortSlots);
@@ -113,7 +127,30 @@ int launch_ph(const float* m0, const float* m1, int n_sets, const Layout& L, int
     TL_CUDA(cudaMemsetAsync(a.job_counter, 0, 256, st));
     long long jobs = (long long)n_sets * L.M;
     int grid = (int)(jobs < kPhSlots ? jobs : kPhSlots);
-    if (dim == 1) tl::ph_kernel<1><<<grid, tl::kPhThreads, 0, st>>>(a);
+    if (L.small) {
+        static int n_sm = 0;
+        if (n_sm == 0) {
+            int dev = 0, v = 0;
+            TL_CUDA(cudaGetDevice(&dev));
+            TL_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+            n_sm = v > 0 ? v : 148;
+        }
+        if (grid > n_sm) grid = n_sm;  // one 1024-thread CTA per SM, work handed out dynamically
+        tl::PhSmallArgs sa;
+        sa.base = a;
+        sa.Bg = at<uint16_t>(ws, L.Bg); sa.rootpix = at<uint32_t>(ws, L.rootpix); sa.zval = at<uint32_t>(ws, L.zval);
+        sa.T2g = at<tl::TEntry>(ws, L.T2g);
+        sa.b_stride = L.b_stride; sa.k_stride = L.k_stride;
+        const char* pe = getenv("TL_PROFILE");
+        sa.prof = (pe && pe[0] == '1') ? at<unsigned long long>(ws, L.counter) + 8 : nullptr;
+        if (dim == 1) {
+            TL_CUDA(cudaFuncSetAttribute(tl::ph_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl::kSmallSmemBytes));
+            tl::ph_small_kernel<1><<<grid, tl::kPhThreads, tl::kSmallSmemBytes, st>>>(sa);
+        } else {
+            TL_CUDA(cudaFuncSetAttribute(tl::ph_small_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl::kSmallSmemBytes));
+            tl::ph_small_kernel<0><<<grid, tl::kPhThreads, tl::kSmallSmemBytes, st>>>(sa);
+        }
+    } else if (dim == 1) tl::ph_kernel<1><<<grid, tl::kPhThreads, 0, st>>>(a);
     else tl::ph_kernel<0><<<grid, tl::kPhThreads, 0, st>>>(a);
     TL_CUDA(cudaGetLastError());
     return TL_OK;
@@ -152,6 +189,15 @@ extern "C" {
 int tl_version(void) { return TL_ABI_VERSION; }
 
 const char* tl_last_error(void) { return g_err; }
+
+/* Debug aid (not part of the hot path): copies the 8 phase cycle counters that the persistence
+ * kernel accumulates when the environment has TL_PROFILE=1.  Synchronises the device. */
+int tl_debug_profile(const void* ws, unsigned long long* host_out8) {
+    if (!ws || !host_out8) return fail(TL_ERR_ARG, "null pointer");
+    TL_CUDA(cudaDeviceSynchronize());
+    TL_CUDA(cudaMemcpy(host_out8, static_cast<const char*>(ws) + 64, 64, cudaMemcpyDeviceToHost));
+    return TL_OK;
+}
 
 int tl_max_pairs(int H, int W, int dim) {
     if (H <= 0 || W <= 0 || (dim != 0 && dim != 1)) return fail(TL_ERR_ARG, "bad arguments");
@@ -225,9 +271,6 @@ int tl_backward(const float* grad_loss, const void* ws, size_t ws_bytes, int B, 
     TL_CUDA(cudaGetLastError());
     return TL_OK;
 }
-
-int tl_persistence_pairs(const float* maps, int n_maps, int H, int W, int dim, void* ws, size_t ws_bytes,
-                         int32_t* pairs, int cap, int32_t* counts, void* stream);
 
 }  // extern "C"
 

@@ -44,7 +44,7 @@ def make_labels(B: int, H: int, W: int, gen: torch.Generator, n_classes: int = N
     rows = torch.arange(H, device=dev, dtype=torch.float32).view(H, 1)
     cols = torch.arange(W, device=dev, dtype=torch.float32).view(1, W)
     for b in range(B):
-        n_layers = int(torch.randint(9, n_classes, (1,), generator=gen, device=dev))
+        n_layers = int(torch.randint(min(9, n_classes - 1), n_classes, (1,), generator=gen, device=dev))
         # interfaces: cumulative sums of positive low-pass 1-D noise
         raw = torch.rand((n_layers + 1, W + 32), generator=gen, device=dev)
         k = _gauss1d(max(2.0, W / 16), dev)

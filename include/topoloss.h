@@ -116,6 +116,13 @@ int tl_wasserstein(const float* D1, const int32_t* off1, const float* D2, const 
                    int n_diag, int max_rows1, int max_rows2, float q,
                    void* ws, size_t ws_bytes, double* cost, int32_t* match1, void* stream);
 
+/*
+ * Debug aid, not on the hot path: host copy of the 8 per-phase cycle counters the persistence
+ * kernel accumulates into the workspace when the process environment has TL_PROFILE=1.
+ * Synchronises the device.  host_out8: 8 x uint64 on the host.
+ */
+int tl_debug_profile(const void* ws, unsigned long long* host_out8);
+
 /* Bytes of workspace tl_wasserstein needs. */
 int tl_wasserstein_workspace_bytes(int n_diag, int max_rows1, int max_rows2, size_t* bytes);
 

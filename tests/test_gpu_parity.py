@@ -73,6 +73,24 @@ def test_pairs_signed_and_negative_zero(dim):
     _assert_same_pairs(maps, dim)
 
 
+@pytest.mark.parametrize("dim", [0, 1])
+def test_pairs_large_map_global_kernel(dim):
+    """> 65535 nodes: the global-memory kernel (ph_kernel) instead of the shared-memory one."""
+    rng = np.random.default_rng(5)
+    maps = rng.random((3, 300, 300)).astype(np.float32)
+    maps[2] = np.round(maps[2] * 8) / 8
+    _assert_same_pairs(maps, dim)
+
+
+def test_pairs_many_basins_table_spills_to_global():
+    """A checkerboard has ~N/2 basins: the triplet table no longer fits shared memory."""
+    rng = np.random.default_rng(6)
+    yy, xx = np.mgrid[0:256, 0:256]
+    board = ((yy + xx) % 2).astype(np.float32)
+    maps = np.stack([board + 0.25 * rng.random((256, 256)).astype(np.float32), board]).astype(np.float32)
+    _assert_same_pairs(maps, 1)
+
+
 def test_pairs_repeatable():
     rng = np.random.default_rng(11)
     maps = rng.random((6, 96, 96)).astype(np.float32)
