@@ -53,6 +53,16 @@ struct Ph {
         }
     }
 
+    // read-only variant for the flatten pass (a halving store there could regress an entry that
+    // another thread has already pointed at the root)
+    __device__ __forceinline__ int find0_ro(int x) const {
+        for (;;) {
+            const uint64_t t = ld_cg_u64(T + x);
+            if ((uint32_t)(t >> 32) != kCodeL0) return x;
+            x = (int)(uint32_t)t;
+        }
+    }
+
     // level-0 union: link the younger root under the elder one
     __device__ void union0(int a, int b) {
         for (;;) {
@@ -190,7 +200,7 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
         __syncthreads();
         // flatten level-0 chains so that later finds are one hop
         for (int x = tid; x < n_real; x += nt) {
-            int r = ph.find0(x);
+            int r = ph.find0_ro(x);
             if (r != x) T[x] = ((uint64_t)kCodeL0 << 32) | (uint32_t)r;
         }
         __syncthreads();

@@ -131,6 +131,14 @@ struct SmallCtx {
         }
         return x;
     }
+    // read-only find for the flatten pass: a halving store there could land after another thread
+    // has already flattened that entry and regress it to a non-root ancestor
+    __device__ __forceinline__ uint32_t find_ro(uint32_t x) const {
+        const volatile uint16_t* p = par;
+        uint32_t px = p[x];
+        while (px != x) { x = px; px = p[x]; }
+        return x;
+    }
     __device__ __forceinline__ bool elder(uint32_t x, uint32_t y) const {
         if (DIM == 1) {
             if (x == kOut16) return true;
@@ -255,7 +263,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         __syncthreads();
         TL_PROF(1);
         for (int x = tid; x < n_real; x += nt) {
-            const uint32_t r = cx.find((uint32_t)x);
+            const uint32_t r = cx.find_ro((uint32_t)x);
             par[x] = (uint16_t)r;
         }
         __syncthreads();
