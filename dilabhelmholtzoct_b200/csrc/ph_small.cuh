@@ -78,28 +78,53 @@ __device__ __forceinline__ bool basin_elder(uint32_t x, uint32_t zx, uint32_t y,
     return zx != zy ? zx < zy : x < y;
 }
 
+#ifdef TL_STATS
+#define TL_STAT(i) (++g_stats_local[i])
+__device__ unsigned long long g_stats[8];
+#else
+#define TL_STAT(i) ((void)0)
+#endif
+
 template <bool SM>
-__device__ __forceinline__ uint32_t rep2(const TEntry* T, uint32_t x, uint64_t skey, TEntry& entry) {
+__device__ __forceinline__ uint32_t rep2(const TEntry* T, uint32_t x, uint64_t skey, TEntry& entry
+#ifdef TL_STATS
+                                         , unsigned* g_stats_local
+#endif
+) {
     for (;;) {
+        TL_STAT(0);
         const TEntry e = t_load<SM>(T + x);
         if (e.ekey > skey) { entry = e; return x; }
         x = e.target;
     }
 }
 
+#ifdef TL_STATS
+#define TL_SARG , g_stats_local
+#define TL_SPARAM , unsigned* g_stats_local
+#else
+#define TL_SARG
+#define TL_SPARAM
+#endif
+
 template <int DIM, bool SM>
-__device__ void merge2(TEntry* T, uint32_t a, uint32_t b, uint64_t skey) {
+__device__ void merge2(TEntry* T, uint32_t a, uint32_t b, uint64_t skey TL_SPARAM) {
+    TL_STAT(1);
     for (;;) {
         TEntry ea, eb;
-        uint32_t x = rep2<SM>(T, a, skey, ea), y = rep2<SM>(T, b, skey, eb);
+        TL_STAT(2);
+        uint32_t x = rep2<SM>(T, a, skey, ea TL_SARG), y = rep2<SM>(T, b, skey, eb TL_SARG);
         if (x == y) return;
+        TL_STAT(3);
         if (basin_elder<DIM>(y, eb.zval, x, ea.zval)) { uint32_t t = x; x = y; y = t; eb = ea; }
         TEntry want;
         want.ekey = skey; want.target = x; want.zval = eb.zval;
         if (t_cas<SM>(T + y, eb, want)) {
             if (eb.ekey == kRootKey) return;
+            TL_STAT(4);
             a = x; b = eb.target; skey = eb.ekey;  // re-assert y's former connection for x
         } else {
+            TL_STAT(5);
             a = x; b = y;
         }
     }
@@ -177,6 +202,9 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
     uint32_t* zvalg = S.zval + (size_t)blockIdx.x * S.k_stride;
     const unsigned int n_jobs = (unsigned)A.n_sets * (unsigned)A.n_maps;
     long long t0 = 0;
+#ifdef TL_STATS
+    unsigned g_stats_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 #define TL_PROF(slot)                                                        \
     do {                                                                     \
         if (S.prof && tid == 0) { long long t1 = clock64(); atomicAdd(S.prof + (slot), (unsigned long long)(t1 - t0)); t0 = t1; } \
@@ -262,11 +290,17 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         }
         __syncthreads();
         TL_PROF(1);
-        for (int x = tid; x < n_real; x += nt) {
-            const uint32_t r = cx.find_ro((uint32_t)x);
-            par[x] = (uint16_t)r;
+        // flatten by pointer jumping: each round every node adopts its grandparent (own entry only,
+        // so no store can regress another thread's result); depth halves per round
+        for (;;) {
+            int changed = 0;
+            for (int x = tid; x < n_real; x += nt) {
+                const uint32_t p = par[x];
+                const uint32_t gp = par[p];
+                if (gp != p) { par[x] = (uint16_t)gp; changed = 1; }
+            }
+            if (!__syncthreads_or(changed)) break;
         }
-        __syncthreads();
         TL_PROF(2);
 
         // ---- census: dense basin ids in raster order of the roots
@@ -352,9 +386,13 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             if (la == lb) continue;
             const float val = is_v ? g.vedge_val(ei, ej) : g.hedge_val(ei, ej);
             const uint64_t skey = g.make_ekey(val, pos);
-            if (t_in_smem) merge2<DIM, true>(T, la, lb, skey);
-            else merge2<DIM, false>(T, la, lb, skey);
+            if (t_in_smem) merge2<DIM, true>(T, la, lb, skey TL_SARG);
+            else merge2<DIM, false>(T, la, lb, skey TL_SARG);
         }
+#ifdef TL_STATS
+        for (int i = 0; i < 8; ++i) if (g_stats_local[i]) { atomicAdd(&g_stats[i], (unsigned long long)g_stats_local[i]); g_stats_local[i] = 0; }
+        if (tid == 0) { atomicAdd(&g_stats[6], (unsigned long long)K); atomicAdd(&g_stats[7], 1ull); }
+#endif
         __syncthreads();
         TL_PROF(4);
 

@@ -199,6 +199,15 @@ int tl_debug_profile(const void* ws, unsigned long long* host_out8) {
     return TL_OK;
 }
 
+#ifdef TL_STATS
+int tl_debug_stats(unsigned long long* host_out8, int reset) {
+    TL_CUDA(cudaDeviceSynchronize());
+    TL_CUDA(cudaMemcpyFromSymbol(host_out8, tl::g_stats, 64));
+    if (reset) { unsigned long long z[8] = {0}; TL_CUDA(cudaMemcpyToSymbol(tl::g_stats, z, 64)); }
+    return TL_OK;
+}
+#endif
+
 int tl_max_pairs(int H, int W, int dim) {
     if (H <= 0 || W <= 0 || (dim != 0 && dim != 1)) return fail(TL_ERR_ARG, "bad arguments");
     return max_pairs(H, W, dim);

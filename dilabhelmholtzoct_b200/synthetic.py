@@ -62,7 +62,7 @@ def make_labels(B: int, H: int, W: int, gen: torch.Generator, n_classes: int = N
             u = torch.rand(5, generator=gen, device=dev)
             cy, cx = H * (0.2 + 0.6 * float(u[0])), W * (0.1 + 0.8 * float(u[1]))
             ry, rx = max(1.5, H * (0.01 + 0.05 * float(u[2]))), max(1.5, W * (0.015 + 0.08 * float(u[3])))
-            cls = (3, 4, 7)[int(float(u[4]) * 3) % 3]
+            cls = (3, 4, 7)[int(float(u[4]) * 3) % 3] % max(1, n_classes - 1)
             inside = ((rows - cy) / ry) ** 2 + ((cols - cx) / rx) ** 2 <= 1.0
             lab = torch.where(inside, torch.full_like(lab, cls), lab)
         labels[b] = lab
