@@ -238,55 +238,59 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
 
         // ---- phase 1: level-0 union-find in shared memory
         const bool alias = DIM == 1 && N == 65536;  // last pixel == OUTSIDE
-        for (int x = tid; x < n_real; x += nt) {
-            if (alias && x == N - 1) continue;
-            uint64_t best = ~0ull;
+        const FastDiv divW((uint32_t)W), divVW((uint32_t)VW), divW1((uint32_t)(W + 1));
+        for (int x0 = warp * 32; x0 < n_real; x0 += nt) {  // warp-uniform trip count
+            const int x = x0 + lane;
             int other = -1;
-            if (DIM == 1) {
-                const int r = x / W, c = x - r * W;
-                const float fp = g.px(r, c);
-                {
-                    float v = r == 0 ? fp : fminf(fp, g.px(r - 1, c));
-                    uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 1 + (2 * r) * GW));
-                    if (k < best) { best = k; other = r == 0 ? (int)kOut16 : x - W; }
-                }
-                {
-                    float v = r == H - 1 ? fp : fminf(fp, g.px(r + 1, c));
-                    uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 1 + (2 * r + 2) * GW));
-                    if (k < best) { best = k; other = r == H - 1 ? (int)kOut16 : x + W; }
-                }
-                {
-                    float v = c == 0 ? fp : fminf(fp, g.px(r, c - 1));
-                    uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + (2 * r + 1) * GW));
-                    if (k < best) { best = k; other = c == 0 ? (int)kOut16 : x - 1; }
-                }
-                {
-                    float v = c == W - 1 ? fp : fminf(fp, g.px(r, c + 1));
-                    uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 2 + (2 * r + 1) * GW));
-                    if (k < best) { best = k; other = c == W - 1 ? (int)kOut16 : x + 1; }
-                }
-                if ((uint32_t)(best >> 32) != (uint32_t)(g.make_ekey(fp, 0u) >> 32)) other = -1;  // strict local max
-                if (alias && other == N - 1) other = (int)kOut16;
-            } else {
-                const int i = x / VW, j = x - i * VW;
-                if (i > 0) {
-                    uint64_t k = g.make_ekey(g.vedge_val(i - 1, j), (uint32_t)(2 * j + (2 * i - 1) * GW));
-                    if (k < best) { best = k; other = x - VW; }
-                }
-                if (i < H) {
-                    uint64_t k = g.make_ekey(g.vedge_val(i, j), (uint32_t)(2 * j + (2 * i + 1) * GW));
-                    if (k < best) { best = k; other = x + VW; }
-                }
-                if (j > 0) {
-                    uint64_t k = g.make_ekey(g.hedge_val(i, j - 1), (uint32_t)(2 * j - 1 + (2 * i) * GW));
-                    if (k < best) { best = k; other = x - 1; }
-                }
-                if (j < W) {
-                    uint64_t k = g.make_ekey(g.hedge_val(i, j), (uint32_t)(2 * j + 1 + (2 * i) * GW));
-                    if (k < best) { best = k; other = x + 1; }
+            if (x < n_real && !(alias && x == N - 1)) {
+                uint64_t best = ~0ull;
+                if (DIM == 1) {
+                    const int r = (int)divW.div((uint32_t)x), c = x - r * W;
+                    const float fp = g.px(r, c);
+                    {
+                        float v = r == 0 ? fp : fminf(fp, g.px(r - 1, c));
+                        uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 1 + (2 * r) * GW));
+                        if (k < best) { best = k; other = r == 0 ? (int)kOut16 : x - W; }
+                    }
+                    {
+                        float v = r == H - 1 ? fp : fminf(fp, g.px(r + 1, c));
+                        uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 1 + (2 * r + 2) * GW));
+                        if (k < best) { best = k; other = r == H - 1 ? (int)kOut16 : x + W; }
+                    }
+                    {
+                        float v = c == 0 ? fp : fminf(fp, g.px(r, c - 1));
+                        uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + (2 * r + 1) * GW));
+                        if (k < best) { best = k; other = c == 0 ? (int)kOut16 : x - 1; }
+                    }
+                    {
+                        float v = c == W - 1 ? fp : fminf(fp, g.px(r, c + 1));
+                        uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 2 + (2 * r + 1) * GW));
+                        if (k < best) { best = k; other = c == W - 1 ? (int)kOut16 : x + 1; }
+                    }
+                    if ((uint32_t)(best >> 32) != (uint32_t)(g.make_ekey(fp, 0u) >> 32)) other = -1;  // strict local max
+                    if (alias && other == N - 1) other = (int)kOut16;
+                } else {
+                    const int i = (int)divVW.div((uint32_t)x), j = x - i * VW;
+                    if (i > 0) {
+                        uint64_t k = g.make_ekey(g.vedge_val(i - 1, j), (uint32_t)(2 * j + (2 * i - 1) * GW));
+                        if (k < best) { best = k; other = x - VW; }
+                    }
+                    if (i < H) {
+                        uint64_t k = g.make_ekey(g.vedge_val(i, j), (uint32_t)(2 * j + (2 * i + 1) * GW));
+                        if (k < best) { best = k; other = x + VW; }
+                    }
+                    if (j > 0) {
+                        uint64_t k = g.make_ekey(g.hedge_val(i, j - 1), (uint32_t)(2 * j - 1 + (2 * i) * GW));
+                        if (k < best) { best = k; other = x - 1; }
+                    }
+                    if (j < W) {
+                        uint64_t k = g.make_ekey(g.hedge_val(i, j), (uint32_t)(2 * j + 1 + (2 * i) * GW));
+                        if (k < best) { best = k; other = x + 1; }
+                    }
                 }
             }
             if (other >= 0) cx.union0((uint32_t)x, (uint32_t)other);
+            __syncwarp();  // reconverge: without it the lanes drift apart and replay the loop body per group
         }
         __syncthreads();
         TL_PROF(1);
@@ -365,29 +369,38 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         }
         __syncthreads();
         const int n_vedges = H * (W + 1), n_hedges = (H + 1) * W;
-        for (int e = tid; e < n_vedges + n_hedges; e += nt) {
-            int a, b;
-            uint32_t pos;
-            int ei, ej;
-            const bool is_v = e < n_vedges;
-            if (is_v) {
-                ei = e / (W + 1); ej = e - ei * (W + 1);
-                pos = (uint32_t)(2 * ej + (2 * ei + 1) * GW);
-                if (DIM == 1) { a = ej == 0 ? -1 : ei * W + ej - 1; b = ej == W ? -1 : ei * W + ej; }
-                else { a = ei * VW + ej; b = a + VW; }
-            } else {
-                const int e2 = e - n_vedges;
-                ei = e2 / W; ej = e2 - ei * W;
-                pos = (uint32_t)(2 * ej + 1 + (2 * ei) * GW);
-                if (DIM == 1) { a = ei == 0 ? -1 : (ei - 1) * W + ej; b = ei == H ? -1 : ei * W + ej; }
-                else { a = ei * VW + ej; b = a + 1; }
+        const int n_edges = n_vedges + n_hedges;
+        for (int e0 = warp * 32; e0 < n_edges; e0 += nt) {  // warp-uniform trip count
+            const int e = e0 + lane;
+            uint32_t la = 0u, lb = 0u;
+            uint64_t skey = 0ull;
+            if (e < n_edges) {
+                int a, b, ei, ej;
+                uint32_t pos;
+                const bool is_v = e < n_vedges;
+                if (is_v) {
+                    ei = (int)divW1.div((uint32_t)e); ej = e - ei * (W + 1);
+                    pos = (uint32_t)(2 * ej + (2 * ei + 1) * GW);
+                    if (DIM == 1) { a = ej == 0 ? -1 : ei * W + ej - 1; b = ej == W ? -1 : ei * W + ej; }
+                    else { a = ei * VW + ej; b = a + VW; }
+                } else {
+                    const int e2 = e - n_vedges;
+                    ei = (int)divW.div((uint32_t)e2); ej = e2 - ei * W;
+                    pos = (uint32_t)(2 * ej + 1 + (2 * ei) * GW);
+                    if (DIM == 1) { a = ei == 0 ? -1 : (ei - 1) * W + ej; b = ei == H ? -1 : ei * W + ej; }
+                    else { a = ei * VW + ej; b = a + 1; }
+                }
+                la = a < 0 ? 0u : Bg[a]; lb = b < 0 ? 0u : Bg[b];
+                if (la != lb) {
+                    const float val = is_v ? g.vedge_val(ei, ej) : g.hedge_val(ei, ej);
+                    skey = g.make_ekey(val, pos);
+                }
             }
-            const uint32_t la = a < 0 ? 0u : Bg[a], lb = b < 0 ? 0u : Bg[b];
-            if (la == lb) continue;
-            const float val = is_v ? g.vedge_val(ei, ej) : g.hedge_val(ei, ej);
-            const uint64_t skey = g.make_ekey(val, pos);
-            if (t_in_smem) merge2<DIM, true>(T, la, lb, skey TL_SARG);
-            else merge2<DIM, false>(T, la, lb, skey TL_SARG);
+            if (la != lb) {
+                if (t_in_smem) merge2<DIM, true>(T, la, lb, skey TL_SARG);
+                else merge2<DIM, false>(T, la, lb, skey TL_SARG);
+            }
+            __syncwarp();  // reconverge before the next batch of 32 edges
         }
 #ifdef TL_STATS
         for (int i = 0; i < 8; ++i) if (g_stats_local[i]) { atomicAdd(&g_stats[i], (unsigned long long)g_stats_local[i]); g_stats_local[i] = 0; }

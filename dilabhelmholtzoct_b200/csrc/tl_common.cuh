@@ -38,6 +38,15 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
+// Exact n / d for n < 2^22, d <= 4097 via multiply-shift (magic = ceil(2^40 / d)); avoids the
+// ~30-instruction integer division in the per-node / per-edge loops.
+struct FastDiv {
+    uint64_t magic;
+    uint32_t d;
+    __host__ __device__ explicit FastDiv(uint32_t d_) : magic(((1ull << 40) + d_ - 1) / d_), d(d_) {}
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return (uint32_t)(((uint64_t)n * magic) >> 40); }
+};
+
 // Triplet-table entry: high 32 bits = merge code, low 32 bits = target node.
 //   code 0            : level-0 link (merged before every recorded edge; always followed)
 //   code 0xFFFFFFFF   : root (never merged)
