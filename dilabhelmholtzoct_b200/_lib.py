@@ -26,6 +26,9 @@ SIGNATURES = {
                                             ctypes.c_int, c_fp, c_fp]),
     "tl_wasserstein": (ctypes.c_int, [c_fp] * 4 + [ctypes.c_int] * 3 + [ctypes.c_float, c_fp,
                                       ctypes.c_size_t, c_fp, c_fp, c_fp]),
+    "tl_timing_enable": (ctypes.c_int, [ctypes.c_int]),
+    "tl_timing_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
+    "tl_debug_profile": (ctypes.c_int, [c_fp, ctypes.POINTER(ctypes.c_ulonglong)]),
     "tl_wasserstein_workspace_bytes": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_size_t)]),
 }
 

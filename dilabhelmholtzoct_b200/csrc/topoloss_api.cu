@@ -32,6 +32,29 @@ int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(TL_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
+// Optional per-kernel timing (bench.py's roofline): when enabled on this thread, tl_forward and
+// tl_backward bracket each kernel with cudaEventRecord on the caller's stream.  Events are created
+// lazily and reused; nothing is synchronised until tl_timing_read.
+constexpr int kStages = 6;        // ph, sort, match, loss, grad-zero, grad-scatter
+constexpr int kTimingRing = 128;  // calls remembered between two reads
+struct Timing {
+    bool on = false;
+    int n_fwd = 0, n_bwd = 0;
+    cudaEvent_t ev[kTimingRing][kStages + 2] = {};
+    bool have[kTimingRing] = {};
+};
+Timing g_timing;  // process-wide: tl_backward runs on autograd's worker thread
+
+cudaEvent_t timing_event(int call, int idx) {
+    Timing& t = g_timing;
+    if (!t.have[call]) {
+        for (int i = 0; i < kStages + 2; ++i) cudaEventCreate(&t.ev[call][i]);
+        t.have[call] = true;
+    }
+    return t.ev[call][idx];
+}
+#define TL_MARK(call, idx, st) do { if (g_timing.on && (call) < kTimingRing) cudaEventRecord(timing_event((call), (idx)), (st)); } while (0)
+
 constexpr int kPhSlots = 296;     // CTAs of the persistence kernel (2 per SM on a 148-SM B200)
 constexpr int kSortSlots = 296;
 constexpr int kMatchSlots = 296;
@@ -199,6 +222,31 @@ int tl_debug_profile(const void* ws, unsigned long long* host_out8) {
     return TL_OK;
 }
 
+int tl_timing_enable(int on) {
+    g_timing.on = on != 0;
+    g_timing.n_fwd = g_timing.n_bwd = 0;
+    return TL_OK;
+}
+
+int tl_timing_read(float* ms_sum6, int* n_calls) {
+    if (!ms_sum6 || !n_calls) return fail(TL_ERR_ARG, "null pointer");
+    Timing& t = g_timing;
+    for (int i = 0; i < kStages; ++i) ms_sum6[i] = 0.f;
+    const int nf = t.n_fwd < kTimingRing ? t.n_fwd : kTimingRing;
+    const int nb = t.n_bwd < kTimingRing ? t.n_bwd : kTimingRing;
+    for (int c = 0; c < nf; ++c) {
+        TL_CUDA(cudaEventSynchronize(t.ev[c][4]));
+        for (int i = 0; i < 4; ++i) { float ms = 0.f; TL_CUDA(cudaEventElapsedTime(&ms, t.ev[c][i], t.ev[c][i + 1])); ms_sum6[i] += ms; }
+    }
+    for (int c = 0; c < nb; ++c) {
+        TL_CUDA(cudaEventSynchronize(t.ev[c][7]));
+        for (int i = 4; i < 6; ++i) { float ms = 0.f; TL_CUDA(cudaEventElapsedTime(&ms, t.ev[c][i + 1], t.ev[c][i + 2])); ms_sum6[i] += ms; }
+    }
+    n_calls[0] = nf; n_calls[1] = nb;
+    t.n_fwd = t.n_bwd = 0;
+    return TL_OK;
+}
+
 #ifdef TL_STATS
 int tl_debug_stats(unsigned long long* host_out8, int reset) {
     TL_CUDA(cudaDeviceSynchronize());
@@ -233,10 +281,14 @@ int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W
     if (ws_bytes < L.total) return fail(TL_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, L.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
+    const int call = g_timing.n_fwd;
+    TL_MARK(call, 0, st);
     rc = launch_ph(pred, truth, 2, L, H, W, feat_d, ws, st);
     if (rc != TL_OK) return rc;
+    TL_MARK(call, 1, st);
     rc = launch_sort(2, L, ws, st);
     if (rc != TL_OK) return rc;
+    TL_MARK(call, 2, st);
 
     tl::MatchArgs m;
     m.d1 = tl::Diagrams{reinterpret_cast<const char*>(at<tl::PairRec>(ws, L.pairs[0])) + offsetof(tl::PairRec, b),
@@ -250,6 +302,7 @@ int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W
     fill_match_scratch(m, ws, L.v, L.minv, L.u, L.way, L.pcol, L.used, L.stride_c, L.stride_r);
     tl::match_kernel<<<L.M < kMatchSlots ? L.M : kMatchSlots, tl::kMatchThreads, 0, st>>>(m);
     TL_CUDA(cudaGetLastError());
+    TL_MARK(call, 3, st);
 
     tl::LossArgs la;
     la.cost = m.cost; la.tpers = m.tpers; la.B = B; la.C = C; la.B_global = B_global; la.loss_r = loss_r;
@@ -270,7 +323,10 @@ int tl_backward(const float* grad_loss, const void* ws, size_t ws_bytes, int B, 
     if (ws_bytes < L.total) return fail(TL_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, L.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     void* w = const_cast<void*>(ws);
+    const int call = g_timing.n_bwd;
+    TL_MARK(call, 5, st);
     TL_CUDA(cudaMemsetAsync(grad_pred, 0, sizeof(float) * (size_t)B * C * H * W, st));
+    TL_MARK(call, 6, st);
     tl::GradArgs g;
     g.pairs = at<tl::PairRec>(w, L.pairs[0]); g.counts = at<int32_t>(w, L.counts[0]);
     g.coef = at<double>(w, L.coef); g.grad_loss = grad_loss;
@@ -278,6 +334,8 @@ int tl_backward(const float* grad_loss, const void* ws, size_t ws_bytes, int B, 
     g.q = q; g.lamda = lamda; g.grad_pred = grad_pred;
     tl::grad_kernel<<<L.M < 1184 ? L.M : 1184, 256, 0, st>>>(g);
     TL_CUDA(cudaGetLastError());
+    TL_MARK(call, 7, st);
+    if (g_timing.on) ++g_timing.n_bwd;
     return TL_OK;
 }
 

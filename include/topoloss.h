@@ -123,6 +123,17 @@ int tl_wasserstein(const float* D1, const int32_t* off1, const float* D2, const 
  */
 int tl_debug_profile(const void* ws, unsigned long long* host_out8);
 
+/*
+ * Measurement aid for bench.py's roofline: while enabled on the calling thread, tl_forward and
+ * tl_backward bracket each of their kernels with cudaEventRecord on the caller's stream (the
+ * stream the kernels are launched on).  tl_timing_read synchronises those events and returns, on
+ * the host, the summed milliseconds of the 6 stages [persistence, segmented sort, matching, loss,
+ * grad zero-fill, grad scatter] over the calls since the last enable/read (at most 128), and the
+ * number of forward / backward calls in n_calls[0..1].
+ */
+int tl_timing_enable(int on);
+int tl_timing_read(float* ms_sum6, int* n_calls);
+
 /* Bytes of workspace tl_wasserstein needs. */
 int tl_wasserstein_workspace_bytes(int n_diag, int max_rows1, int max_rows2, size_t* bytes);
 

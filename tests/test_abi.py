@@ -1,0 +1,67 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/topoloss.h declares;
+host-only entry points validate their arguments.  No compute call is made here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "topoloss.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tl_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = _declared()
+    for must in ["tl_forward", "tl_backward", "tl_workspace_bytes", "tl_persistence_pairs", "tl_wasserstein",
+                 "tl_last_error", "tl_version"]:
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from dilabhelmholtzoct_b200 import _lib, build
+    if not os.path.exists(build.LIB_PATH):
+        build.build()
+    L = ctypes.CDLL(build.LIB_PATH)
+    for name in _declared():
+        assert hasattr(L, name), f"{name} declared in topoloss.h but not exported"
+    assert _lib.lib().tl_version() == _lib.ABI_VERSION
+    assert set(_lib.SIGNATURES) <= set(_declared())
+
+
+def test_workspace_bytes_and_argument_errors():
+    from dilabhelmholtzoct_b200 import _lib
+    L = _lib.lib()
+    n = ctypes.c_size_t(0)
+    assert L.tl_workspace_bytes(64, 14, 256, 256, 1, ctypes.byref(n)) == 0 and n.value > 64 * 14 * 256 * 256
+    small = ctypes.c_size_t(0)
+    assert L.tl_workspace_bytes(2, 14, 50, 50, 1, ctypes.byref(small)) == 0 and small.value < n.value
+    assert L.tl_workspace_bytes(2, 14, 50, 50, 2, ctypes.byref(n)) == -1      # feat_d = 2 is invalid on 2-D maps
+    assert b"feat_d" in L.tl_last_error()
+    assert L.tl_workspace_bytes(2, 14, 50, 60, 1, ctypes.byref(n)) == -1      # non-square
+    assert L.tl_workspace_bytes(0, 14, 50, 50, 1, ctypes.byref(n)) == -1
+    assert L.tl_max_pairs(256, 256, 1) == 256 * 256 // 2 + 2
+    with pytest.raises(ValueError):
+        _lib.check(-1, "x")
+    with pytest.raises(RuntimeError):
+        _lib.check(-3, "x")
+
+
+def test_product_has_no_cpu_path_and_never_imports_the_oracle():
+    import torch
+    import dilabhelmholtzoct_b200 as tlb
+    x = torch.rand(2, 2, 8, 8)
+    with pytest.raises(ValueError, match="CUDA"):
+        tlb.topo_loss(x, x, 0.1, feat_d=1)
+    assert tlb.topo_loss(x, x, 0.0) == 0.0  # the reference's early-out returns a Python float
+    pkg = os.path.join(ROOT, "dilabhelmholtzoct_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "topo_oracle" not in text, f

@@ -227,3 +227,47 @@ def test_zero_cost_gives_nan_grad():
     assert float(loss) == 0.0
     g = p.grad
     assert torch.isnan(g).any() and not torch.isnan(g).all()
+
+
+def test_golden_fixture_on_gpu():
+    import json, os
+    data = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pairs_small.json")))
+    for case in data["pairs"]:
+        f = np.array(case["image"], dtype=np.float32)
+        assert _gpu_pairs(f[None], 0)[0].tolist() == case["h0"]
+        assert _gpu_pairs(f[None], 1)[0].tolist() == case["h1"]
+    for case in data["losses"]:
+        pred, truth = torch.tensor(case["pred"]), torch.tensor(case["truth"])
+        loss, grad = _loss_and_grad(pred, truth, case["lamda"], feat_d=case["feat_d"], loss_q=case["q"])
+        assert abs(loss - case["loss"]) <= REL * abs(case["loss"])
+        g = np.array(case["grad"], np.float32)
+        assert np.abs(grad - g).max() <= REL * np.abs(g).max() + 1e-12
+
+
+def test_sharded_wrapper_matches_unsharded_on_gpu():
+    """Shards run one after the other on one device (B_global passed to the kernel) must add up to
+    the unsharded loss and reproduce its gradient."""
+    import dilabhelmholtzoct_b200 as tlb
+    from dilabhelmholtzoct_b200.parallel import shard_batch, topo_loss_sharded
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(4, 64, 64, seed=21, n_classes=3)
+    full_loss, full_grad = _loss_and_grad(pred, truth, 0.1, feat_d=1)
+    total, grads = 0.0, []
+    for r in range(2):
+        sl = shard_batch(4, r, 2)
+        p = pred[sl].cuda().requires_grad_(True)
+        part = topo_loss_sharded(p, truth[sl].cuda(), 0.1, feat_d=1, global_batch=4)
+        part.backward()
+        total += float(part)
+        grads.append(p.grad.cpu().numpy())
+    assert abs(total - full_loss) <= REL * abs(full_loss)
+    assert np.abs(np.concatenate(grads) - full_grad).max() <= REL * np.abs(full_grad).max()
+
+
+def test_forward_is_deterministic():
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(2, 128, 128, seed=5, n_classes=6)
+    a = _loss_and_grad(pred, truth, 0.1, feat_d=1)
+    for _ in range(3):
+        b = _loss_and_grad(pred, truth, 0.1, feat_d=1)
+        assert a[0] == b[0] and np.array_equal(a[1] != 0, b[1] != 0)

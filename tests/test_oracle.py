@@ -1,0 +1,157 @@
+"""CPU suite: pins the fast oracle (oracle/topo_oracle.c) against the literal cell-complex
+restatement, the hand-derived KATs, scipy's exact assignment and a torch-autograd restatement of
+torch_topological's WassersteinDistance.  (The reference itself has no tests -- SURVEY.md 8c.)"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+from scipy.optimize import linear_sum_assignment
+
+import oracle
+from oracle.oracle_literal import cubical_pairs_literal
+from tests.kats import KATS
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pairs_small.json")
+
+
+@pytest.mark.parametrize("name", sorted(KATS))
+def test_kats_literal_and_fast(name):
+    img, h0, h1, ess = KATS[name]
+    f = np.array(img, dtype=np.float32)
+    l0, l1, less = cubical_pairs_literal(f)
+    assert sorted(l0) == sorted(h0) and sorted(l1) == sorted(h1) and less == ess
+    f0 = [tuple(x) for x in oracle.cubical_pairs(f, 0)]
+    f1 = [tuple(x) for x in oracle.cubical_pairs(f, 1)]
+    assert f0 == l0 + [less] and f1 == l1
+
+
+def test_golden_fixture_matches_fast_oracle():
+    data = json.load(open(GOLDEN))
+    for case in data["pairs"]:
+        f = np.array(case["image"], dtype=np.float32)
+        assert oracle.cubical_pairs(f, 0).tolist() == case["h0"]
+        assert oracle.cubical_pairs(f, 1).tolist() == case["h1"]
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 9), st.integers(1, 9), st.integers(0, 2), st.integers(0, 2 ** 31 - 1))
+def test_fast_equals_literal(h, w, mode, seed):
+    rng = np.random.default_rng(seed)
+    f = (rng.random((h, w)) if mode == 0 else rng.integers(0, [0, 4, 2][mode], (h, w))).astype(np.float32)
+    l0, l1, ess = cubical_pairs_literal(f)
+    assert [tuple(x) for x in oracle.cubical_pairs(f, 0)] == l0 + [ess]
+    assert [tuple(x) for x in oracle.cubical_pairs(f, 1)] == l1
+
+
+def _torch_cost_matrix(D1, D2, q):
+    """torch_topological WassersteinDistance._make_distance_matrix, restated."""
+    def proj(d):
+        x, y = d[:, 0], d[:, 1]
+        return 0.5 * torch.stack(((x + y), (x + y)), 1)
+    d11 = torch.linalg.vector_norm(D1 - proj(D1), float("inf"), dim=1)
+    d22 = torch.linalg.vector_norm(D2 - proj(D2), float("inf"), dim=1)
+    dist = torch.cdist(D1, D2, p=float("inf"))
+    up = torch.hstack((dist, d11[:, None]))
+    lo = torch.cat((d22, torch.tensor(0.0).unsqueeze(0)))
+    return torch.vstack((up, lo)).pow(q)
+
+
+def _diagrams(rng, n, m, binary_truth=False):
+    b = rng.random(n).astype(np.float32)
+    D1 = np.stack([b, b + rng.random(n).astype(np.float32)], 1).reshape(-1, 2)
+    b = rng.random(m).astype(np.float32)
+    D2 = np.stack([b, b + rng.random(m).astype(np.float32)], 1).reshape(-1, 2)
+    if binary_truth and m:
+        D2[:] = np.array([0.0, 1.0], np.float32)
+    return D1, D2
+
+
+@pytest.mark.parametrize("q", [1, 2, 3])
+def test_wasserstein_is_the_exact_lp_optimum(q):
+    rng = np.random.default_rng(q)
+    for t in range(120):
+        n, m = int(rng.integers(0, 10)), int(rng.integers(0, 10))
+        D1, D2 = _diagrams(rng, n, m, t % 5 == 0)
+        cost, match = oracle.wasserstein(D1, D2, q)
+        M = _torch_cost_matrix(torch.tensor(D1), torch.tensor(D2), q).double().numpy()
+        big = np.full((n + m, n + m), 1e9)
+        big[:n, :m] = M[:n, :m]
+        for i in range(n):
+            big[i, m + i] = M[i, m]
+        for j in range(m):
+            big[n + j, j] = M[n, j]
+        big[n:, m:] = 0.0
+        ref = big[linear_sum_assignment(big)].sum() if n + m else 0.0
+        assert abs(cost - ref) < 1e-6
+        # the returned matching attains the reported cost
+        tot = sum(M[i, match[i]] if match[i] >= 0 else M[i, m] for i in range(n))
+        tot += sum(M[n, j] for j in range(m) if j not in set(match[match >= 0].tolist()))
+        assert abs(tot - cost) < 1e-6
+
+
+def test_kat_w2_toy_and_gradient_tie():
+    cost, match = oracle.wasserstein(np.array([[0.2, 0.8]], np.float32), np.array([[0.0, 1.0]], np.float32), 2)
+    assert abs(cost - 0.04) < 1e-7 and match[0] == 0  # W = 0.2, not 0.34 via the diagonal
+    D1 = torch.tensor([[0.25, 0.75]], requires_grad=True)
+    M = _torch_cost_matrix(D1, torch.tensor([[0.0, 1.0]]), 2)
+    M[0, 0].backward()
+    assert torch.allclose(D1.grad, torch.tensor([[0.5, -0.5]]))  # both coordinates at an exact L-inf tie
+
+
+@pytest.mark.parametrize("feat_d", [0, 1])
+@pytest.mark.parametrize("q", [1, 2])
+def test_loss_and_gradient_match_torch_autograd_restatement(feat_d, q):
+    """Full path restated with torch autograd (gather -> cost matrix -> plan . M -> pow(1/q) -> mean),
+    using the oracle's pairs and matching as the (non-differentiable) combinatorial part."""
+    rng = np.random.default_rng(10 * feat_d + q)
+    B, C, n = 2, 3, 10
+    pred = rng.random((B, C, n, n)).astype(np.float32)
+    truth = (np.round(rng.random((B, C, n, n)) * 3) / 3).astype(np.float32)
+    lam = 0.1
+    loss, grad, _ = oracle.topo_loss(pred, truth, lam, feat_d=feat_d, loss_q=q)
+    x = torch.tensor(pred, requires_grad=True)
+    per_image = []
+    for b in range(B):
+        total = 0.0
+        for c in range(C):
+            p1 = torch.as_tensor(oracle.cubical_pairs(pred[b, c], feat_d), dtype=torch.long)
+            p2 = torch.as_tensor(oracle.cubical_pairs(truth[b, c], feat_d), dtype=torch.long)
+            xf, tf = x[b, c].ravel(), torch.tensor(truth[b, c]).ravel()
+            D1 = torch.stack((xf[p1[:, 0]], xf[p1[:, 1]]), 1)
+            D2 = torch.stack((tf[p2[:, 0]], tf[p2[:, 1]]), 1)
+            M = _torch_cost_matrix(D1, D2, q)
+            _, match = oracle.wasserstein(D1.detach().numpy(), D2.numpy(), q)
+            G = torch.zeros_like(M)
+            for i, j in enumerate(match):
+                G[i, j if j >= 0 else len(D2)] = 1.0
+            used = set(match[match >= 0].tolist())
+            for j in range(len(D2)):
+                if j not in used:
+                    G[len(D1), j] = 1.0
+            total = total + (G * M).sum()
+        per_image.append(total.pow(1.0 / q))
+    ref = lam * torch.stack(per_image).mean()
+    ref.backward()
+    assert abs(float(ref) - loss) <= 1e-5 * abs(loss)
+    assert np.abs(x.grad.numpy() - grad).max() <= 1e-5 * np.abs(grad).max()
+
+
+def test_golden_losses():
+    data = json.load(open(GOLDEN))
+    for case in data["losses"]:
+        loss, grad, _ = oracle.topo_loss(np.array(case["pred"], np.float32), np.array(case["truth"], np.float32),
+                                         case["lamda"], feat_d=case["feat_d"], loss_q=case["q"])
+        assert abs(loss - case["loss"]) <= 1e-6 * abs(case["loss"])
+        assert np.allclose(grad, np.array(case["grad"], np.float32), rtol=1e-6, atol=1e-9)
+
+
+def test_threads_do_not_change_the_result():
+    rng = np.random.default_rng(2)
+    pred = rng.random((2, 4, 24, 24)).astype(np.float32)
+    truth = (rng.random((2, 4, 24, 24)) < 0.4).astype(np.float32)
+    a = oracle.topo_loss(pred, truth, 0.1, feat_d=1, nthreads=1)
+    b = oracle.topo_loss(pred, truth, 0.1, feat_d=1, nthreads=4)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
