@@ -130,8 +130,15 @@ __device__ void merge2(TEntry* T, uint32_t a, uint32_t b, uint64_t skey TL_SPARA
     }
 }
 
+struct __align__(16) CrossEdge {
+    uint64_t skey;
+    uint32_t la, lb;
+};
+
 struct PhSmallArgs {
     PhArgs base;
+    CrossEdge* elist;    // [grid][e_stride] edges that cross two basins
+    size_t e_stride;
     uint16_t* Bg;        // [grid][b_stride] basin id per node
     uint32_t* rootpix;   // [grid][k_stride] root node of each basin
     uint32_t* zval;      // [grid][k_stride]
@@ -187,7 +194,7 @@ template <int DIM>
 __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned int s_job;
-    __shared__ int s_count, s_K;
+    __shared__ int s_count, s_K, s_ncross;
     __shared__ unsigned long long s_argmax;
     __shared__ int s_wcnt[kPhThreads / 32];
     const PhArgs& A = S.base;
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_job = atomicAdd(A.job_counter, 1u); s_count = 0; s_argmax = 0ull; }
+        if (tid == 0) { s_job = atomicAdd(A.job_counter, 1u); s_count = 0; s_ncross = 0; s_argmax = 0ull; }
         __syncthreads();
         const unsigned int job = s_job;
         if (job >= n_jobs) break;
@@ -370,6 +377,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         __syncthreads();
         const int n_vedges = H * (W + 1), n_hedges = (H + 1) * W;
         const int n_edges = n_vedges + n_hedges;
+        // pass 1 (streaming): compact the edges that cross two basins into a per-CTA list
+        CrossEdge* elist = S.elist + (size_t)blockIdx.x * S.e_stride;
         for (int e0 = warp * 32; e0 < n_edges; e0 += nt) {  // warp-uniform trip count
             const int e = e0 + lane;
             uint32_t la = 0u, lb = 0u;
@@ -396,11 +405,35 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     skey = g.make_ekey(val, pos);
                 }
             }
-            if (la != lb) {
-                if (t_in_smem) merge2<DIM, true>(T, la, lb, skey TL_SARG);
-                else merge2<DIM, false>(T, la, lb, skey TL_SARG);
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, la != lb);
+            if (bal) {
+                int base = 0;
+                const int leader = __ffs(bal) - 1;
+                if (lane == leader) base = atomicAdd(&s_ncross, __popc(bal));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (la != lb) {
+                    CrossEdge ce;
+                    ce.skey = skey; ce.la = la; ce.lb = lb;
+                    elist[base + __popc(bal & lanemask_lt())] = ce;
+                }
             }
-            __syncwarp();  // reconverge before the next batch of 32 edges
+        }
+        __syncthreads();
+        // pass 2: every lane owns a contiguous chunk of the list, so all lanes have work and
+        // concurrently processed edges are far apart (few CAS conflicts on the same basins)
+        {
+            const int n_cross = s_ncross;
+            const int per = (n_cross + nt - 1) / nt;
+            const int i_beg = min(n_cross, tid * per), i_end = min(n_cross, i_beg + per);
+            for (int k = 0; k < per; ++k) {  // block-uniform trip count
+                const int i = i_beg + k;
+                if (i < i_end) {
+                    const CrossEdge ce = elist[i];
+                    if (t_in_smem) merge2<DIM, true>(T, ce.la, ce.lb, ce.skey TL_SARG);
+                    else merge2<DIM, false>(T, ce.la, ce.lb, ce.skey TL_SARG);
+                }
+                __syncwarp();  // reconverge before the next edge
+            }
         }
 #ifdef TL_STATS
         for (int i = 0; i < 8; ++i) if (g_stats_local[i]) { atomicAdd(&g_stats[i], (unsigned long long)g_stats_local[i]); g_stats_local[i] = 0; }

@@ -56,6 +56,7 @@ cudaEvent_t timing_event(int call, int idx) {
 #define TL_MARK(call, idx, st) do { if (g_timing.on && (call) < kTimingRing) cudaEventRecord(timing_event((call), (idx)), (st)); } while (0)
 
 constexpr int kPhSlots = 296;     // CTAs of the persistence kernel (2 per SM on a 148-SM B200)
+constexpr int kSmallSlots = 160;   // >= SM count: one 1024-thread CTA per SM in ph_small_kernel
 constexpr int kSortSlots = 296;
 constexpr int kMatchSlots = 296;
 
@@ -72,7 +73,7 @@ struct Layout {
     size_t counter, counts[2], cost, tpers, coef, pairs[2], skeys[2], match1;
     size_t T, t_stride;
     int small;  // 1: shared-memory persistence kernel (<= 65535 nodes)
-    size_t Bg, b_stride, rootpix, zval, T2g, k_stride;
+    size_t Bg, b_stride, rootpix, zval, T2g, k_stride, elist, e_stride;
     size_t key_tmp, idx_a, idx_b, rec_tmp;
     size_t v, minv, u, way, pcol, used, stride_c, stride_r;
     size_t total;
@@ -99,10 +100,12 @@ Layout make_layout(int M, int H, int W, int dim, int B) {
     if (L.small) {
         L.b_stride = align_up(sizeof(uint16_t) * (size_t)L.n_nodes) / sizeof(uint16_t);
         L.k_stride = align_up((size_t)L.cap + 2, 64);
-        L.Bg = take(sizeof(uint16_t) * L.b_stride * kPhSlots);
-        L.rootpix = take(sizeof(uint32_t) * L.k_stride * kPhSlots);
-        L.zval = take(sizeof(uint32_t) * L.k_stride * kPhSlots);
-        L.T2g = take(sizeof(tl::TEntry) * L.k_stride * kPhSlots);
+        L.Bg = take(sizeof(uint16_t) * L.b_stride * kSmallSlots);
+        L.rootpix = take(sizeof(uint32_t) * L.k_stride * kSmallSlots);
+        L.zval = take(sizeof(uint32_t) * L.k_stride * kSmallSlots);
+        L.T2g = take(sizeof(tl::TEntry) * L.k_stride * kSmallSlots);
+        L.e_stride = align_up((size_t)H * (W + 1) + (size_t)(H + 1) * W, 64);
+        L.elist = take(sizeof(tl::CrossEdge) * L.e_stride * kSmallSlots);
     } else {
         L.t_stride = align_up(sizeof(uint64_t) * (size_t)L.n_nodes) / sizeof(uint64_t);
         L.T = take(sizeof(uint64_t) * L.t_stride * kPhSlots);
@@ -159,11 +162,13 @@ int launch_ph(const float* m0, const float* m1, int n_sets, const Layout& L, int
             n_sm = v > 0 ? v : 148;
         }
         if (grid > n_sm) grid = n_sm;  // one 1024-thread CTA per SM, work handed out dynamically
+        if (grid > kSmallSlots) grid = kSmallSlots;
         tl::PhSmallArgs sa;
         sa.base = a;
         sa.Bg = at<uint16_t>(ws, L.Bg); sa.rootpix = at<uint32_t>(ws, L.rootpix); sa.zval = at<uint32_t>(ws, L.zval);
         sa.T2g = at<tl::TEntry>(ws, L.T2g);
         sa.b_stride = L.b_stride; sa.k_stride = L.k_stride;
+        sa.elist = at<tl::CrossEdge>(ws, L.elist); sa.e_stride = L.e_stride;
         const char* pe = getenv("TL_PROFILE");
         sa.prof = (pe && pe[0] == '1') ? at<unsigned long long>(ws, L.counter) + 8 : nullptr;
         if (dim == 1) {
@@ -309,7 +314,8 @@ int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W
     la.q = q; la.lamda = lamda; la.loss_out = loss_out; la.coef = at<double>(ws, L.coef);
     tl::loss_kernel<<<1, 256, 0, st>>>(la);
     TL_CUDA(cudaGetLastError());
-
+    TL_MARK(call, 4, st);
+    if (g_timing.on) ++g_timing.n_fwd;
     return TL_OK;
 }
 
