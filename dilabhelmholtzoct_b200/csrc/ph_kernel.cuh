@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
     __shared__ unsigned int s_job;
     __shared__ int s_count;
     __shared__ unsigned long long s_argmax;
+    __shared__ int s_wcnt[kPhThreads / 32];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int H = A.H, W = A.W, N = H * W;
     uint64_t* T = A.T + (size_t)blockIdx.x * A.t_stride;
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
         // ---- phase 3: emit pairs of positive persistence
         PairRec* out = A.pairs[set] + (size_t)map * A.cap;
         uint64_t* skeys = A.skeys[set] ? A.skeys[set] + (size_t)map * A.cap : nullptr;
+        int emit_base = 0;
         for (int x0 = 0; x0 < NN; x0 += nt) {
             const int x = x0 + tid;
             bool emit = false;
@@ -259,25 +261,26 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
                     sk = ~0ull;
                 }
             }
-            // warp-aggregated slot allocation
+            // deterministic slots: block-wide scan in node (= raster) order, no atomics
             const unsigned ballot = __ballot_sync(0xFFFFFFFFu, emit);
-            if (ballot) {
-                int base = 0;
-                const int lane = tid & 31, leader = __ffs(ballot) - 1;
-                if (lane == leader) base = atomicAdd(&s_count, __popc(ballot));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (emit) {
-                    const int slot = base + __popc(ballot & lanemask_lt());
-                    if (slot < A.cap) {
-                        rec.b = __ldg(g.f + rec.cre);
-                        rec.d = __ldg(g.f + rec.des);
-                        rec.tb = rec.td = __int_as_float(0x7FC00000);
-                        out[slot] = rec;
-                        if (skeys) skeys[slot] = sk;
-                    }
+            if ((tid & 31) == 0) s_wcnt[tid >> 5] = __popc(ballot);
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int w = 0; w < kPhThreads / 32; ++w) { const int v = s_wcnt[w]; total += v; if (w < (tid >> 5)) before += v; }
+            if (emit) {
+                const int slot = emit_base + before + __popc(ballot & lanemask_lt());
+                if (slot < A.cap) {
+                    rec.b = __ldg(g.f + rec.cre);
+                    rec.d = __ldg(g.f + rec.des);
+                    rec.tb = rec.td = __int_as_float(0x7FC00000);
+                    out[slot] = rec;
+                    if (skeys) skeys[slot] = sk;
                 }
             }
+            emit_base += total;
+            __syncthreads();
         }
+        if (tid == 0) s_count = emit_base;
         __syncthreads();
         if (tid == 0) A.counts[set][map] = s_count;
     }

@@ -31,14 +31,20 @@ struct __align__(16) TEntry {
     uint32_t zval;    // ordered value of this basin's eldest node (immutable)
 };
 
+// Triplet table handle: a generic pointer (global fallback) plus the 32-bit shared-window address
+// of the same table, computed once, so the hot loops index shared memory without cvta.
+struct TRef {
+    TEntry* g;
+    uint32_t s;
+};
+
 template <bool SM>
-__device__ __forceinline__ TEntry t_load(const TEntry* p) {
+__device__ __forceinline__ TEntry t_load(const TRef& T, uint32_t x) {
     uint32_t a, b, c, d;
     if (SM) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
-        asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(sa) : "memory");
+        asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(T.s + x * 16u) : "memory");
     } else {
-        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(T.g + x) : "memory");
     }
     TEntry e;
     e.ekey = (uint64_t)a | ((uint64_t)b << 32);
@@ -48,21 +54,20 @@ __device__ __forceinline__ TEntry t_load(const TEntry* p) {
 }
 
 template <bool SM>
-__device__ __forceinline__ bool t_cas(TEntry* p, const TEntry& expect, const TEntry& want) {
+__device__ __forceinline__ bool t_cas(const TRef& T, uint32_t x, const TEntry& expect, const TEntry& want) {
     const uint64_t e_hi = (uint64_t)expect.target | ((uint64_t)expect.zval << 32);
     const uint64_t d_hi = (uint64_t)want.target | ((uint64_t)want.zval << 32);
     uint64_t o_lo, o_hi;
     if (SM) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
         asm volatile(
             "{\n .reg .b128 e, d, o;\n mov.b128 e, {%3, %4};\n mov.b128 d, {%5, %6};\n"
             " atom.shared.cas.b128 o, [%2], e, d;\n mov.b128 {%0, %1}, o;\n}\n"
-            : "=l"(o_lo), "=l"(o_hi) : "r"(sa), "l"(expect.ekey), "l"(e_hi), "l"(want.ekey), "l"(d_hi) : "memory");
+            : "=l"(o_lo), "=l"(o_hi) : "r"(T.s + x * 16u), "l"(expect.ekey), "l"(e_hi), "l"(want.ekey), "l"(d_hi) : "memory");
     } else {
         asm volatile(
             "{\n .reg .b128 e, d, o;\n mov.b128 e, {%3, %4};\n mov.b128 d, {%5, %6};\n"
             " atom.global.cas.b128 o, [%2], e, d;\n mov.b128 {%0, %1}, o;\n}\n"
-            : "=l"(o_lo), "=l"(o_hi) : "l"(p), "l"(expect.ekey), "l"(e_hi), "l"(want.ekey), "l"(d_hi) : "memory");
+            : "=l"(o_lo), "=l"(o_hi) : "l"(T.g + x), "l"(expect.ekey), "l"(e_hi), "l"(want.ekey), "l"(d_hi) : "memory");
     }
     return o_lo == expect.ekey && o_hi == e_hi;
 }
@@ -86,14 +91,14 @@ __device__ unsigned long long g_stats[8];
 #endif
 
 template <bool SM>
-__device__ __forceinline__ uint32_t rep2(const TEntry* T, uint32_t x, uint64_t skey, TEntry& entry
+__device__ __forceinline__ uint32_t rep2(const TRef& T, uint32_t x, uint64_t skey, TEntry& entry
 #ifdef TL_STATS
                                          , unsigned* g_stats_local
 #endif
 ) {
     for (;;) {
         TL_STAT(0);
-        const TEntry e = t_load<SM>(T + x);
+        const TEntry e = t_load<SM>(T, x);
         if (e.ekey > skey) { entry = e; return x; }
         x = e.target;
     }
@@ -108,7 +113,7 @@ __device__ __forceinline__ uint32_t rep2(const TEntry* T, uint32_t x, uint64_t s
 #endif
 
 template <int DIM, bool SM>
-__device__ void merge2(TEntry* T, uint32_t a, uint32_t b, uint64_t skey TL_SPARAM) {
+__device__ void merge2(const TRef& T, uint32_t a, uint32_t b, uint64_t skey TL_SPARAM) {
     TL_STAT(1);
     for (;;) {
         TEntry ea, eb;
@@ -119,7 +124,7 @@ __device__ void merge2(TEntry* T, uint32_t a, uint32_t b, uint64_t skey TL_SPARA
         if (basin_elder<DIM>(y, eb.zval, x, ea.zval)) { uint32_t t = x; x = y; y = t; eb = ea; }
         TEntry want;
         want.ekey = skey; want.target = x; want.zval = eb.zval;
-        if (t_cas<SM>(T + y, eb, want)) {
+        if (t_cas<SM>(T, y, eb, want)) {
             if (eb.ekey == kRootKey) return;
             TL_STAT(4);
             a = x; b = eb.target; skey = eb.ekey;  // re-assert y's former connection for x
@@ -368,11 +373,13 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
 
         // ---- phase B: triplet merge tree over basins
         const bool t_in_smem = K + 1 <= t_cap_smem;
-        TEntry* T = t_in_smem ? Ts : S.T2g + (size_t)blockIdx.x * S.k_stride;
+        TRef T;
+        T.g = t_in_smem ? Ts : S.T2g + (size_t)blockIdx.x * S.k_stride;
+        T.s = (uint32_t)__cvta_generic_to_shared(Ts);
         for (int c = tid; c <= K; c += nt) {
             TEntry e;
             e.ekey = kRootKey; e.target = (uint32_t)c; e.zval = c ? zvalg[c] : 0u;
-            T[c] = e;
+            T.g[c] = e;
         }
         __syncthreads();
         const int n_vedges = H * (W + 1), n_hedges = (H + 1) * W;
@@ -445,13 +452,14 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         // ---- emit
         PairRec* out = A.pairs[set] + (size_t)map * A.cap;
         uint64_t* skeys = A.skeys[set] ? A.skeys[set] + (size_t)map * A.cap : nullptr;
+        int emit_base = 0;
         for (int c0 = 1; c0 <= K; c0 += nt) {
             const int c = c0 + tid;
             bool emit = false;
             PairRec rec;
             uint64_t sk = 0;
             if (c <= K) {
-                const TEntry e = t_in_smem ? t_load<true>(T + c) : t_load<false>(T + c);
+                const TEntry e = t_in_smem ? t_load<true>(T, (uint32_t)c) : t_load<false>(T, (uint32_t)c);
                 const int x = (int)rootpix[c];
                 if (e.ekey != kRootKey) {
                     if ((uint32_t)(e.ekey >> 32) != e.zval) {
@@ -473,24 +481,26 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     sk = ~0ull;
                 }
             }
+            // deterministic slots: block-wide scan in basin (= raster) order, no atomics
             const unsigned ballot = __ballot_sync(0xFFFFFFFFu, emit);
-            if (ballot) {
-                int base = 0;
-                const int leader = __ffs(ballot) - 1;
-                if (lane == leader) base = atomicAdd(&s_count, __popc(ballot));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (emit) {
-                    const int slot = base + __popc(ballot & lanemask_lt());
-                    if (slot < A.cap) {
-                        rec.b = __ldg(g.f + rec.cre);
-                        rec.d = __ldg(g.f + rec.des);
-                        rec.tb = rec.td = __int_as_float(0x7FC00000);
-                        out[slot] = rec;
-                        if (skeys) skeys[slot] = sk;
-                    }
+            if (lane == 0) s_wcnt[warp] = __popc(ballot);
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int w = 0; w < kPhThreads / 32; ++w) { const int v = s_wcnt[w]; total += v; if (w < warp) before += v; }
+            if (emit) {
+                const int slot = emit_base + before + __popc(ballot & lanemask_lt());
+                if (slot < A.cap) {
+                    rec.b = __ldg(g.f + rec.cre);
+                    rec.d = __ldg(g.f + rec.des);
+                    rec.tb = rec.td = __int_as_float(0x7FC00000);
+                    out[slot] = rec;
+                    if (skeys) skeys[slot] = sk;
                 }
             }
+            emit_base += total;
+            __syncthreads();
         }
+        if (tid == 0) s_count = emit_base;
         __syncthreads();
         if (tid == 0) A.counts[set][map] = s_count;
         TL_PROF(5);

@@ -139,12 +139,12 @@ template <typename T>
 T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
 
 int launch_ph(const float* m0, const float* m1, int n_sets, const Layout& L, int H, int W, int dim,
-              void* ws, cudaStream_t st) {
+              void* ws, cudaStream_t st, bool want_sort_keys) {
     tl::PhArgs a;
     a.maps[0] = m0; a.maps[1] = m1;
     for (int s = 0; s < 2; ++s) {
         a.pairs[s] = at<tl::PairRec>(ws, L.pairs[s]);
-        a.skeys[s] = at<uint64_t>(ws, L.skeys[s]);
+        a.skeys[s] = want_sort_keys ? at<uint64_t>(ws, L.skeys[s]) : nullptr;
         a.counts[s] = at<int32_t>(ws, L.counts[s]);
     }
     a.n_sets = n_sets; a.n_maps = L.M; a.H = H; a.W = W; a.cap = L.cap;
@@ -288,11 +288,11 @@ int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W
 
     const int call = g_timing.n_fwd;
     TL_MARK(call, 0, st);
-    rc = launch_ph(pred, truth, 2, L, H, W, feat_d, ws, st);
+    // pairs leave the persistence kernel in a deterministic (raster) order, so the matching needs no
+    // sort; the segmented sort only serves tl_persistence_pairs (gudhi's emission order)
+    rc = launch_ph(pred, truth, 2, L, H, W, feat_d, ws, st, false);
     if (rc != TL_OK) return rc;
     TL_MARK(call, 1, st);
-    rc = launch_sort(2, L, ws, st);
-    if (rc != TL_OK) return rc;
     TL_MARK(call, 2, st);
 
     tl::MatchArgs m;
@@ -375,7 +375,7 @@ int tl_persistence_pairs(const float* maps, int n_maps, int H, int W, int dim, v
     const Layout L = make_layout(n_maps, H, W, dim, n_maps);
     if (ws_bytes < L.total) return fail(TL_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, L.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rc = launch_ph(maps, nullptr, 1, L, H, W, dim, ws, st);
+    rc = launch_ph(maps, nullptr, 1, L, H, W, dim, ws, st, true);
     if (rc != TL_OK) return rc;
     rc = launch_sort(1, L, ws, st);
     if (rc != TL_OK) return rc;
