@@ -38,6 +38,15 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _host_cores() -> int:
+    """Threads the CPU arm uses: every core this process may run on.  (torchrun exports
+    OMP_NUM_THREADS=1; the oracle's num_threads() clause overrides it.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -49,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -60,6 +69,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """Start of the timed region: samples before this point are dropped (if any remain after)."""
+        self.first = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -68,6 +81,8 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        if len(self.rows) > getattr(self, "first", 0):
+            self.rows = self.rows[getattr(self, "first", 0):]
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -98,7 +113,7 @@ def run_reference(args, rank, world):
     import torch
     import oracle
     from dilabhelmholtzoct_b200.synthetic import make_batch
-    cores = min(oracle.max_threads(), os.cpu_count() or 1)
+    cores = _host_cores()
     sample = args.ref_images
     pred, truth = make_batch(sample, H, W, seed=1234 + 1000 * 2, device="cpu")
     value, dt = cpu_arm(pred, truth, cores, args.steps, max(1, min(args.warmup, 2)))
@@ -196,11 +211,14 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.mark()
     L.tl_timing_enable(1)
     ms_step = timed(step_resident, args.steps)
     sums = (ctypes.c_float * 6)()
@@ -251,7 +269,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         import oracle
-        cores = min(oracle.max_threads(), os.cpu_count() or 1)
+        cores = _host_cores()
         n = min(args.cpu_sample, B)
         v, dt = cpu_arm(pred_h[:n], truth_h[:n], cores, 1, 0)
         line["cpu_baseline"] = {"value": v, "unit": "masks/s", "cores": cores, "kind": "port",

@@ -83,27 +83,13 @@ __device__ __forceinline__ bool basin_elder(uint32_t x, uint32_t zx, uint32_t y,
     return zx != zy ? zx < zy : x < y;
 }
 
+
 #ifdef TL_STATS
 #define TL_STAT(i) (++g_stats_local[i])
 __device__ unsigned long long g_stats[8];
 #else
 #define TL_STAT(i) ((void)0)
 #endif
-
-template <bool SM>
-__device__ __forceinline__ uint32_t rep2(const TRef& T, uint32_t x, uint64_t skey, TEntry& entry
-#ifdef TL_STATS
-                                         , unsigned* g_stats_local
-#endif
-) {
-    for (;;) {
-        TL_STAT(0);
-        const TEntry e = t_load<SM>(T, x);
-        if (e.ekey > skey) { entry = e; return x; }
-        x = e.target;
-    }
-}
-
 #ifdef TL_STATS
 #define TL_SARG , g_stats_local
 #define TL_SPARAM , unsigned* g_stats_local
@@ -112,33 +98,67 @@ __device__ __forceinline__ uint32_t rep2(const TRef& T, uint32_t x, uint64_t ske
 #define TL_SPARAM
 #endif
 
-template <int DIM, bool SM>
-__device__ void merge2(const TRef& T, uint32_t a, uint32_t b, uint64_t skey TL_SPARAM) {
-    TL_STAT(1);
-    for (;;) {
-        TEntry ea, eb;
-        TL_STAT(2);
-        uint32_t x = rep2<SM>(T, a, skey, ea TL_SARG), y = rep2<SM>(T, b, skey, eb TL_SARG);
-        if (x == y) return;
-        TL_STAT(3);
-        if (basin_elder<DIM>(y, eb.zval, x, ea.zval)) { uint32_t t = x; x = y; y = t; eb = ea; }
-        TEntry want;
-        want.ekey = skey; want.target = x; want.zval = eb.zval;
-        if (t_cas<SM>(T, y, eb, want)) {
-            if (eb.ekey == kRootKey) return;
-            TL_STAT(4);
-            a = x; b = eb.target; skey = eb.ekey;  // re-assert y's former connection for x
-        } else {
-            TL_STAT(5);
-            a = x; b = y;
-        }
-    }
-}
-
 struct __align__(16) CrossEdge {
     uint64_t skey;
     uint32_t la, lb;
 };
+
+// Lock-free Merge of the edges elist[i..i_end) of this lane, as a state machine executed in lock
+// step by the warp.  Per lane: (x, y) are the current nodes of the two walks, doneA/doneB tell
+// whether the representative at level skey has been reached (ea / eb hold its entry).
+template <int DIM, bool SM>
+__device__ __forceinline__ void merge_lanes(const TRef& T, const CrossEdge* __restrict__ elist, int i, int i_end TL_SPARAM) {
+    uint32_t x = 0u, y = 0u;
+    uint64_t skey = 0ull;
+    TEntry ea, eb;
+    ea.ekey = eb.ekey = 0ull; ea.target = eb.target = 0u; ea.zval = eb.zval = 0u;
+    bool active = false, doneA = true, doneB = true;
+    CrossEdge nxt;
+    nxt.skey = 0ull; nxt.la = nxt.lb = 0u;
+    bool have_next = i < i_end;
+    if (have_next) nxt = elist[i];
+    for (;;) {
+        if (!active && have_next) {
+            x = nxt.la; y = nxt.lb; skey = nxt.skey;
+            doneA = doneB = false; active = true;
+            TL_STAT(1);
+            ++i;
+            have_next = i < i_end;
+            if (have_next) nxt = elist[i];  // prefetch: consumed several iterations from now
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        if (active) {
+            if (!doneA) { TL_STAT(0); ea = t_load<SM>(T, x); }
+            if (!doneB) { TL_STAT(0); eb = t_load<SM>(T, y); }
+            if (!doneA) { if (ea.ekey > skey) doneA = true; else x = ea.target; }
+            if (!doneB) { if (eb.ekey > skey) doneB = true; else y = eb.target; }
+            if (doneA && doneB) {
+                TL_STAT(2);
+                if (x == y) {
+                    active = false;
+                } else {
+                    TL_STAT(3);
+                    const bool sw = basin_elder<DIM>(y, eb.zval, x, ea.zval);
+                    const uint32_t xx = sw ? y : x, yy = sw ? x : y;  // yy: the younger representative
+                    const TEntry ey = sw ? ea : eb;
+                    TEntry want;
+                    want.ekey = skey; want.target = xx; want.zval = ey.zval;
+                    if (t_cas<SM>(T, yy, ey, want)) {
+                        if (ey.ekey == kRootKey) {
+                            active = false;
+                        } else {  // re-assert yy's former connection for xx
+                            TL_STAT(4);
+                            x = xx; y = ey.target; skey = ey.ekey; doneA = doneB = false;
+                        }
+                    } else {
+                        TL_STAT(5);
+                        x = xx; y = yy; doneA = doneB = false;
+                    }
+                }
+            }
+        }
+    }
+}
 
 struct PhSmallArgs {
     PhArgs base;
@@ -426,21 +446,18 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             }
         }
         __syncthreads();
-        // pass 2: every lane owns a contiguous chunk of the list, so all lanes have work and
-        // concurrently processed edges are far apart (few CAS conflicts on the same basins)
+        // pass 2: every lane owns a contiguous chunk of the list (all lanes have work; concurrently
+        // processed edges are far apart -> few CAS conflicts).  The merge is a warp-synchronous state
+        // machine: per iteration every active lane advances BOTH representative walks by one hop (two
+        // independent 16-byte loads in flight), so lanes stay converged instead of serialising
+        // differently long walks.
         {
             const int n_cross = s_ncross;
             const int per = (n_cross + nt - 1) / nt;
-            const int i_beg = min(n_cross, tid * per), i_end = min(n_cross, i_beg + per);
-            for (int k = 0; k < per; ++k) {  // block-uniform trip count
-                const int i = i_beg + k;
-                if (i < i_end) {
-                    const CrossEdge ce = elist[i];
-                    if (t_in_smem) merge2<DIM, true>(T, ce.la, ce.lb, ce.skey TL_SARG);
-                    else merge2<DIM, false>(T, ce.la, ce.lb, ce.skey TL_SARG);
-                }
-                __syncwarp();  // reconverge before the next edge
-            }
+            int i = min(n_cross, tid * per);
+            const int i_end = min(n_cross, i + per);
+            if (t_in_smem) merge_lanes<DIM, true>(T, elist, i, i_end TL_SARG);
+            else merge_lanes<DIM, false>(T, elist, i, i_end TL_SARG);
         }
 #ifdef TL_STATS
         for (int i = 0; i < 8; ++i) if (g_stats_local[i]) { atomicAdd(&g_stats[i], (unsigned long long)g_stats_local[i]); g_stats_local[i] = 0; }
