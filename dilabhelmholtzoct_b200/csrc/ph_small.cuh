@@ -271,58 +271,78 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         // ---- phase 1: level-0 union-find in shared memory
         const bool alias = DIM == 1 && N == 65536;  // last pixel == OUTSIDE
         const FastDiv divW((uint32_t)W), divVW((uint32_t)VW), divW1((uint32_t)(W + 1));
-        for (int x0 = warp * 32; x0 < n_real; x0 += nt) {  // warp-uniform trip count
-            const int x = x0 + lane;
-            int other = -1;
-            if (x < n_real && !(alias && x == N - 1)) {
-                uint64_t best = ~0ull;
-                if (DIM == 1) {
-                    const int r = (int)divW.div((uint32_t)x), c = x - r * W;
-                    const float fp = g.px(r, c);
-                    {
-                        float v = r == 0 ? fp : fminf(fp, g.px(r - 1, c));
-                        uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 1 + (2 * r) * GW));
-                        if (k < best) { best = k; other = r == 0 ? (int)kOut16 : x - W; }
-                    }
-                    {
-                        float v = r == H - 1 ? fp : fminf(fp, g.px(r + 1, c));
-                        uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 1 + (2 * r + 2) * GW));
-                        if (k < best) { best = k; other = r == H - 1 ? (int)kOut16 : x + W; }
-                    }
-                    {
-                        float v = c == 0 ? fp : fminf(fp, g.px(r, c - 1));
-                        uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + (2 * r + 1) * GW));
-                        if (k < best) { best = k; other = c == 0 ? (int)kOut16 : x - 1; }
-                    }
-                    {
-                        float v = c == W - 1 ? fp : fminf(fp, g.px(r, c + 1));
-                        uint64_t k = g.make_ekey(v, (uint32_t)(2 * c + 2 + (2 * r + 1) * GW));
-                        if (k < best) { best = k; other = c == W - 1 ? (int)kOut16 : x + 1; }
-                    }
-                    if ((uint32_t)(best >> 32) != (uint32_t)(g.make_ekey(fp, 0u) >> 32)) other = -1;  // strict local max
-                    if (alias && other == N - 1) other = (int)kOut16;
-                } else {
-                    const int i = (int)divVW.div((uint32_t)x), j = x - i * VW;
-                    if (i > 0) {
-                        uint64_t k = g.make_ekey(g.vedge_val(i - 1, j), (uint32_t)(2 * j + (2 * i - 1) * GW));
-                        if (k < best) { best = k; other = x - VW; }
-                    }
-                    if (i < H) {
-                        uint64_t k = g.make_ekey(g.vedge_val(i, j), (uint32_t)(2 * j + (2 * i + 1) * GW));
-                        if (k < best) { best = k; other = x + VW; }
-                    }
-                    if (j > 0) {
-                        uint64_t k = g.make_ekey(g.hedge_val(i, j - 1), (uint32_t)(2 * j - 1 + (2 * i) * GW));
-                        if (k < best) { best = k; other = x - 1; }
-                    }
-                    if (j < W) {
-                        uint64_t k = g.make_ekey(g.hedge_val(i, j), (uint32_t)(2 * j + 1 + (2 * i) * GW));
-                        if (k < best) { best = k; other = x + 1; }
+        // 4 nodes per lane per trip: the 4 x 5 map loads are in flight together (the loop is
+        // latency-bound otherwise); the unions follow, in shared memory
+        for (int x0 = warp * 32; x0 < n_real; x0 += 4 * nt) {  // warp-uniform trip count
+            int other[4];
+            bool strict[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int x = x0 + u * nt + lane;
+                other[u] = -1;
+                strict[u] = false;
+                if (x < n_real && !(alias && x == N - 1)) {
+                    uint64_t best = ~0ull;
+                    if (DIM == 1) {
+                        const int r = (int)divW.div((uint32_t)x), c = x - r * W;
+                        const float fp = g.px(r, c);
+                        const float fu = r == 0 ? fp : g.px(r - 1, c), fd = r == H - 1 ? fp : g.px(r + 1, c);
+                        const float fl = c == 0 ? fp : g.px(r, c - 1), fr = c == W - 1 ? fp : g.px(r, c + 1);
+                        float fo = fp;
+                        {
+                            uint64_t k = g.make_ekey(fminf(fp, fu), (uint32_t)(2 * c + 1 + (2 * r) * GW));
+                            if (k < best) { best = k; other[u] = r == 0 ? (int)kOut16 : x - W; fo = fu; }
+                        }
+                        {
+                            uint64_t k = g.make_ekey(fminf(fp, fd), (uint32_t)(2 * c + 1 + (2 * r + 2) * GW));
+                            if (k < best) { best = k; other[u] = r == H - 1 ? (int)kOut16 : x + W; fo = fd; }
+                        }
+                        {
+                            uint64_t k = g.make_ekey(fminf(fp, fl), (uint32_t)(2 * c + (2 * r + 1) * GW));
+                            if (k < best) { best = k; other[u] = c == 0 ? (int)kOut16 : x - 1; fo = fl; }
+                        }
+                        {
+                            uint64_t k = g.make_ekey(fminf(fp, fr), (uint32_t)(2 * c + 2 + (2 * r + 1) * GW));
+                            if (k < best) { best = k; other[u] = c == W - 1 ? (int)kOut16 : x + 1; fo = fr; }
+                        }
+                        if ((uint32_t)(best >> 32) != (uint32_t)(g.make_ekey(fp, 0u) >> 32)) other[u] = -1;  // strict local max
+                        // the far end is strictly higher (or OUTSIDE): its root is elder than x without any key lookup
+                        strict[u] = other[u] == (int)kOut16 || fo > fp;
+                        if (alias && other[u] == N - 1) { other[u] = (int)kOut16; strict[u] = true; }
+                    } else {
+                        const int i = (int)divVW.div((uint32_t)x), j = x - i * VW;
+                        if (i > 0) {
+                            uint64_t k = g.make_ekey(g.vedge_val(i - 1, j), (uint32_t)(2 * j + (2 * i - 1) * GW));
+                            if (k < best) { best = k; other[u] = x - VW; }
+                        }
+                        if (i < H) {
+                            uint64_t k = g.make_ekey(g.vedge_val(i, j), (uint32_t)(2 * j + (2 * i + 1) * GW));
+                            if (k < best) { best = k; other[u] = x + VW; }
+                        }
+                        if (j > 0) {
+                            uint64_t k = g.make_ekey(g.hedge_val(i, j - 1), (uint32_t)(2 * j - 1 + (2 * i) * GW));
+                            if (k < best) { best = k; other[u] = x - 1; }
+                        }
+                        if (j < W) {
+                            uint64_t k = g.make_ekey(g.hedge_val(i, j), (uint32_t)(2 * j + 1 + (2 * i) * GW));
+                            if (k < best) { best = k; other[u] = x + 1; }
+                        }
                     }
                 }
             }
-            if (other >= 0) cx.union0((uint32_t)x, (uint32_t)other);
-            __syncwarp();  // reconverge: without it the lanes drift apart and replay the loop body per group
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int x = x0 + u * nt + lane;
+                if (other[u] >= 0) {
+                    bool linked = false;
+                    if (strict[u]) {  // x is still a root and every ancestor of `other` is elder than x
+                        const uint32_t rb = cx.find((uint32_t)other[u]);
+                        linked = atomicCAS(reinterpret_cast<unsigned short*>(par + x), (unsigned short)x, (unsigned short)rb) == (unsigned short)x;
+                    }
+                    if (!linked) cx.union0((uint32_t)x, (uint32_t)other[u]);
+                }
+                __syncwarp();  // reconverge: without it the lanes drift apart and replay the loop body per group
+            }
         }
         __syncthreads();
         TL_PROF(1);
@@ -330,6 +350,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         // so no store can regress another thread's result); depth halves per round
         for (;;) {
             int changed = 0;
+#pragma unroll 4
             for (int x = tid; x < n_real; x += nt) {
                 const uint32_t p = par[x];
                 const uint32_t gp = par[p];
@@ -379,6 +400,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             }
         }
         __syncthreads();
+#pragma unroll 4
         for (int x = tid; x < n_real; x += nt) {
             uint32_t b;
             if ((mask[x >> 5] >> (x & 31)) & 1u) b = par[x];
@@ -406,42 +428,50 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         const int n_edges = n_vedges + n_hedges;
         // pass 1 (streaming): compact the edges that cross two basins into a per-CTA list
         CrossEdge* elist = S.elist + (size_t)blockIdx.x * S.e_stride;
-        for (int e0 = warp * 32; e0 < n_edges; e0 += nt) {  // warp-uniform trip count
-            const int e = e0 + lane;
-            uint32_t la = 0u, lb = 0u;
-            uint64_t skey = 0ull;
-            if (e < n_edges) {
-                int a, b, ei, ej;
-                uint32_t pos;
-                const bool is_v = e < n_vedges;
-                if (is_v) {
-                    ei = (int)divW1.div((uint32_t)e); ej = e - ei * (W + 1);
-                    pos = (uint32_t)(2 * ej + (2 * ei + 1) * GW);
-                    if (DIM == 1) { a = ej == 0 ? -1 : ei * W + ej - 1; b = ej == W ? -1 : ei * W + ej; }
-                    else { a = ei * VW + ej; b = a + VW; }
-                } else {
-                    const int e2 = e - n_vedges;
-                    ei = (int)divW.div((uint32_t)e2); ej = e2 - ei * W;
-                    pos = (uint32_t)(2 * ej + 1 + (2 * ei) * GW);
-                    if (DIM == 1) { a = ei == 0 ? -1 : (ei - 1) * W + ej; b = ei == H ? -1 : ei * W + ej; }
-                    else { a = ei * VW + ej; b = a + 1; }
-                }
-                la = a < 0 ? 0u : Bg[a]; lb = b < 0 ? 0u : Bg[b];
-                if (la != lb) {
-                    const float val = is_v ? g.vedge_val(ei, ej) : g.hedge_val(ei, ej);
-                    skey = g.make_ekey(val, pos);
+        for (int e0 = warp * 32; e0 < n_edges; e0 += 4 * nt) {  // warp-uniform trip count, 4 edges per lane
+            uint32_t la[4], lb[4], pos[4];
+            int ei[4], ej[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * nt + lane;
+                la[u] = lb[u] = 0u; pos[u] = 0u; ei[u] = ej[u] = 0;
+                if (e < n_edges) {
+                    int a, b;
+                    if (e < n_vedges) {
+                        ei[u] = (int)divW1.div((uint32_t)e); ej[u] = e - ei[u] * (W + 1);
+                        pos[u] = (uint32_t)(2 * ej[u] + (2 * ei[u] + 1) * GW);
+                        if (DIM == 1) { a = ej[u] == 0 ? -1 : ei[u] * W + ej[u] - 1; b = ej[u] == W ? -1 : ei[u] * W + ej[u]; }
+                        else { a = ei[u] * VW + ej[u]; b = a + VW; }
+                    } else {
+                        const int e2 = e - n_vedges;
+                        ei[u] = (int)divW.div((uint32_t)e2); ej[u] = e2 - ei[u] * W;
+                        pos[u] = (uint32_t)(2 * ej[u] + 1 + (2 * ei[u]) * GW);
+                        if (DIM == 1) { a = ei[u] == 0 ? -1 : (ei[u] - 1) * W + ej[u]; b = ei[u] == H ? -1 : ei[u] * W + ej[u]; }
+                        else { a = ei[u] * VW + ej[u]; b = a + 1; }
+                    }
+                    la[u] = a < 0 ? 0u : Bg[a]; lb[u] = b < 0 ? 0u : Bg[b];
                 }
             }
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, la != lb);
-            if (bal) {
-                int base = 0;
-                const int leader = __ffs(bal) - 1;
-                if (lane == leader) base = atomicAdd(&s_ncross, __popc(bal));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (la != lb) {
-                    CrossEdge ce;
-                    ce.skey = skey; ce.la = la; ce.lb = lb;
-                    elist[base + __popc(bal & lanemask_lt())] = ce;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * nt + lane;
+                const bool cross = la[u] != lb[u];
+                uint64_t skey = 0ull;
+                if (cross) {
+                    const float val = e < n_vedges ? g.vedge_val(ei[u], ej[u]) : g.hedge_val(ei[u], ej[u]);
+                    skey = g.make_ekey(val, pos[u]);
+                }
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, cross);
+                if (bal) {
+                    int base = 0;
+                    const int leader = __ffs(bal) - 1;
+                    if (lane == leader) base = atomicAdd(&s_ncross, __popc(bal));
+                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                    if (cross) {
+                        CrossEdge ce;
+                        ce.skey = skey; ce.la = la[u]; ce.lb = lb[u];
+                        elist[base + __popc(bal & lanemask_lt())] = ce;
+                    }
                 }
             }
         }
