@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
     __shared__ unsigned int s_job;
     __shared__ int s_count, s_K, s_ncross;
     __shared__ unsigned long long s_argmax;
+    __shared__ unsigned int s_lo, s_hi;
     __shared__ int s_wcnt[kPhThreads / 32];
     const PhArgs& A = S.base;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_job = atomicAdd(A.job_counter, 1u); s_count = 0; s_ncross = 0; s_argmax = 0ull; }
+        if (tid == 0) { s_job = atomicAdd(A.job_counter, 1u); s_count = 0; s_ncross = 0; s_argmax = 0ull; s_lo = 0xFFFFFFFFu; s_hi = 0u; }
         __syncthreads();
         const unsigned int job = s_job;
         if (job >= n_jobs) break;
@@ -255,18 +256,42 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         const int NN = g.NN, GW = g.GW, VW = g.VW;
         const int n_real = DIM == 1 ? N : NN;  // nodes that own a slot besides OUTSIDE
 
-        // ---- phase 0
+        // ---- phase 0: init, argmax (H0), and the constant-map shortcut (absent classes give all-zero
+        //      ground-truth maps: no finite pair; H0 keeps only the essential class (0 -> argmax = 0))
         for (int x = tid; x < 65536; x += nt) par[x] = (uint16_t)x;
-        if (DIM == 0) {
+        {
             unsigned long long best = 0ull;
+            uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+#pragma unroll 4
             for (int p = tid; p < N; p += nt) {
-                unsigned long long k = ((unsigned long long)mono32(__ldg(g.f + p)) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)p);
-                best = k > best ? k : best;
+                const uint32_t m = mono32(__ldg(g.f + p));
+                lo = min(lo, m); hi = max(hi, m);
+                if (DIM == 0) {
+                    unsigned long long k = ((unsigned long long)m << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)p);
+                    best = k > best ? k : best;
+                }
             }
-            atomicMax(&s_argmax, best);
+            lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+            if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+            if (DIM == 0) atomicMax(&s_argmax, best);
         }
         __syncthreads();
         TL_PROF(0);
+        if (s_lo == s_hi) {  // block-uniform
+            if (tid == 0) {
+                int cnt = 0;
+                if (DIM == 0 && A.cap > 0) {
+                    PairRec rec;
+                    rec.cre = 0; rec.des = 0; rec.b = rec.d = __ldg(g.f);
+                    rec.tb = rec.td = __int_as_float(0x7FC00000);
+                    A.pairs[set][(size_t)map * A.cap] = rec;
+                    if (A.skeys[set]) A.skeys[set][(size_t)map * A.cap] = ~0ull;
+                    cnt = 1;
+                }
+                A.counts[set][map] = cnt;
+            }
+            continue;
+        }
 
         // ---- phase 1: level-0 union-find in shared memory
         const bool alias = DIM == 1 && N == 65536;  // last pixel == OUTSIDE
@@ -282,34 +307,29 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 other[u] = -1;
                 strict[u] = false;
                 if (x < n_real && !(alias && x == N - 1)) {
-                    uint64_t best = ~0ull;
                     if (DIM == 1) {
                         const int r = (int)divW.div((uint32_t)x), c = x - r * W;
                         const float fp = g.px(r, c);
                         const float fu = r == 0 ? fp : g.px(r - 1, c), fd = r == H - 1 ? fp : g.px(r + 1, c);
                         const float fl = c == 0 ? fp : g.px(r, c - 1), fr = c == W - 1 ? fp : g.px(r, c + 1);
+                        // earliest incident edge in the descending scan = largest (value, position): the
+                        // value is fp whenever the far pixel is >= fp (or the edge is a boundary edge), and
+                        // among those the bitmap position orders bottom > right > left > top
                         float fo = fp;
-                        {
-                            uint64_t k = g.make_ekey(fminf(fp, fu), (uint32_t)(2 * c + 1 + (2 * r) * GW));
-                            if (k < best) { best = k; other[u] = r == 0 ? (int)kOut16 : x - W; fo = fu; }
-                        }
-                        {
-                            uint64_t k = g.make_ekey(fminf(fp, fd), (uint32_t)(2 * c + 1 + (2 * r + 2) * GW));
-                            if (k < best) { best = k; other[u] = r == H - 1 ? (int)kOut16 : x + W; fo = fd; }
-                        }
-                        {
-                            uint64_t k = g.make_ekey(fminf(fp, fl), (uint32_t)(2 * c + (2 * r + 1) * GW));
-                            if (k < best) { best = k; other[u] = c == 0 ? (int)kOut16 : x - 1; fo = fl; }
-                        }
-                        {
-                            uint64_t k = g.make_ekey(fminf(fp, fr), (uint32_t)(2 * c + 2 + (2 * r + 1) * GW));
-                            if (k < best) { best = k; other[u] = c == W - 1 ? (int)kOut16 : x + 1; fo = fr; }
-                        }
-                        if ((uint32_t)(best >> 32) != (uint32_t)(g.make_ekey(fp, 0u) >> 32)) other[u] = -1;  // strict local max
+                        if (r == H - 1) other[u] = (int)kOut16;
+                        else if (fd >= fp) { other[u] = x + W; fo = fd; }
+                        else if (c == W - 1) other[u] = (int)kOut16;
+                        else if (fr >= fp) { other[u] = x + 1; fo = fr; }
+                        else if (c == 0) other[u] = (int)kOut16;
+                        else if (fl >= fp) { other[u] = x - 1; fo = fl; }
+                        else if (r == 0) other[u] = (int)kOut16;
+                        else if (fu >= fp) { other[u] = x - W; fo = fu; }
+                        // else: strict local maximum, stays a root
                         // the far end is strictly higher (or OUTSIDE): its root is elder than x without any key lookup
                         strict[u] = other[u] == (int)kOut16 || fo > fp;
                         if (alias && other[u] == N - 1) { other[u] = (int)kOut16; strict[u] = true; }
                     } else {
+                        uint64_t best = ~0ull;
                         const int i = (int)divVW.div((uint32_t)x), j = x - i * VW;
                         if (i > 0) {
                             uint64_t k = g.make_ekey(g.vedge_val(i - 1, j), (uint32_t)(2 * j + (2 * i - 1) * GW));
@@ -424,53 +444,65 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             T.g[c] = e;
         }
         __syncthreads();
-        const int n_vedges = H * (W + 1), n_hedges = (H + 1) * W;
-        const int n_edges = n_vedges + n_hedges;
         // pass 1 (streaming): compact the edges that cross two basins into a per-CTA list
         CrossEdge* elist = S.elist + (size_t)blockIdx.x * S.e_stride;
-        for (int e0 = warp * 32; e0 < n_edges; e0 += 4 * nt) {  // warp-uniform trip count, 4 edges per lane
-            uint32_t la[4], lb[4], pos[4];
-            int ei[4], ej[4];
+        // every node owns its left/top edge (H1: pixel) or down/right edge (H0: vertex); the last
+        // column / row also own the boundary edges to OUTSIDE (H1).  2 nodes per lane per trip.
+        for (int x0 = warp * 32; x0 < n_real; x0 += 2 * nt) {  // warp-uniform trip count
+            uint32_t lab[2], lo1[2], lo2[2];
+            int rr[2], cc[2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * nt + lane;
-                la[u] = lb[u] = 0u; pos[u] = 0u; ei[u] = ej[u] = 0;
-                if (e < n_edges) {
-                    int a, b;
-                    if (e < n_vedges) {
-                        ei[u] = (int)divW1.div((uint32_t)e); ej[u] = e - ei[u] * (W + 1);
-                        pos[u] = (uint32_t)(2 * ej[u] + (2 * ei[u] + 1) * GW);
-                        if (DIM == 1) { a = ej[u] == 0 ? -1 : ei[u] * W + ej[u] - 1; b = ej[u] == W ? -1 : ei[u] * W + ej[u]; }
-                        else { a = ei[u] * VW + ej[u]; b = a + VW; }
+            for (int u = 0; u < 2; ++u) {
+                const int x = x0 + u * nt + lane;
+                lab[u] = lo1[u] = lo2[u] = 0u; rr[u] = cc[u] = 0;
+                if (x < n_real) {
+                    if (DIM == 1) {
+                        rr[u] = (int)divW.div((uint32_t)x); cc[u] = x - rr[u] * W;
+                        lab[u] = Bg[x];
+                        lo1[u] = cc[u] == 0 ? 0u : Bg[x - 1];   // across the left v-edge
+                        lo2[u] = rr[u] == 0 ? 0u : Bg[x - W];   // across the top h-edge
                     } else {
-                        const int e2 = e - n_vedges;
-                        ei[u] = (int)divW.div((uint32_t)e2); ej[u] = e2 - ei[u] * W;
-                        pos[u] = (uint32_t)(2 * ej[u] + 1 + (2 * ei[u]) * GW);
-                        if (DIM == 1) { a = ei[u] == 0 ? -1 : (ei[u] - 1) * W + ej[u]; b = ei[u] == H ? -1 : ei[u] * W + ej[u]; }
-                        else { a = ei[u] * VW + ej[u]; b = a + 1; }
+                        rr[u] = (int)divVW.div((uint32_t)x); cc[u] = x - rr[u] * VW;
+                        lab[u] = Bg[x];
+                        lo1[u] = rr[u] < H ? Bg[x + VW] : lab[u];  // down v-edge
+                        lo2[u] = cc[u] < W ? Bg[x + 1] : lab[u];   // right h-edge
                     }
-                    la[u] = a < 0 ? 0u : Bg[a]; lb[u] = b < 0 ? 0u : Bg[b];
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * nt + lane;
-                const bool cross = la[u] != lb[u];
-                uint64_t skey = 0ull;
-                if (cross) {
-                    const float val = e < n_vedges ? g.vedge_val(ei[u], ej[u]) : g.hedge_val(ei[u], ej[u]);
-                    skey = g.make_ekey(val, pos[u]);
-                }
-                const unsigned bal = __ballot_sync(0xFFFFFFFFu, cross);
-                if (bal) {
-                    int base = 0;
-                    const int leader = __ffs(bal) - 1;
-                    if (lane == leader) base = atomicAdd(&s_ncross, __popc(bal));
-                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                    if (cross) {
-                        CrossEdge ce;
-                        ce.skey = skey; ce.la = la[u]; ce.lb = lb[u];
-                        elist[base + __popc(bal & lanemask_lt())] = ce;
+            for (int u = 0; u < 2; ++u) {
+                const int x = x0 + u * nt + lane;
+                const bool valid = x < n_real;
+                const int r = rr[u], c = cc[u];
+#pragma unroll
+                for (int k = 0; k < (DIM == 1 ? 4 : 2); ++k) {
+                    // k = 0: v-edge, k = 1: h-edge, k = 2 / 3: right / bottom boundary edges (H1 only)
+                    bool cross = false;
+                    uint32_t lo = 0u, pos = 0u;
+                    float val = 0.f;
+                    if (valid) {
+                        if (DIM == 1) {
+                            if (k == 0) { lo = lo1[u]; cross = lo != lab[u]; pos = (uint32_t)(2 * c + (2 * r + 1) * GW); }
+                            else if (k == 1) { lo = lo2[u]; cross = lo != lab[u]; pos = (uint32_t)(2 * c + 1 + (2 * r) * GW); }
+                            else if (k == 2) { cross = c == W - 1 && lab[u] != 0u; pos = (uint32_t)(2 * W + (2 * r + 1) * GW); }
+                            else { cross = r == H - 1 && lab[u] != 0u; pos = (uint32_t)(2 * c + 1 + (2 * H) * GW); }
+                            if (cross) val = k == 0 ? g.vedge_val(r, c) : k == 1 ? g.hedge_val(r, c) : g.px(r, c);
+                        } else {
+                            if (k == 0) { lo = lo1[u]; cross = lo != lab[u]; pos = (uint32_t)(2 * c + (2 * r + 1) * GW); if (cross) val = g.vedge_val(r, c); }
+                            else { lo = lo2[u]; cross = lo != lab[u]; pos = (uint32_t)(2 * c + 1 + (2 * r) * GW); if (cross) val = g.hedge_val(r, c); }
+                        }
+                    }
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, cross);
+                    if (bal) {
+                        int base = 0;
+                        const int leader = __ffs(bal) - 1;
+                        if (lane == leader) base = atomicAdd(&s_ncross, __popc(bal));
+                        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                        if (cross) {
+                            CrossEdge ce;
+                            ce.skey = g.make_ekey(val, pos); ce.la = lo; ce.lb = lab[u];
+                            elist[base + __popc(bal & lanemask_lt())] = ce;
+                        }
                     }
                 }
             }
