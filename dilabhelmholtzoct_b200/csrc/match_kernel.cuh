@@ -16,7 +16,7 @@
 
 namespace tl {
 
-constexpr int kMatchThreads = 256;
+constexpr int kMatchThreads = 1024;
 
 __device__ __forceinline__ float powq(float x, float q) { return q == 2.0f ? x * x : powf(x, q); }
 // torch.cdist(p=inf) entry, then .pow(q)
@@ -102,11 +102,12 @@ __global__ void __launch_bounds__(kMatchThreads) match_kernel(MatchArgs A) {
         int32_t* match1 = A.match1 + (A.d1.off ? A.d1.off[k] : k * A.d1.cap);
 
         double part = 0.0, tp = 0.0;
+#pragma unroll 4
         for (int c = tid; c < Cn; c += nt) { float2 p = row_at(rC, stC, c); part += (double)cost_diag(p.x, p.y, q); }
-        for (int i = tid; i < n; i += nt) {
-            match1[i] = -1;
-            if (A.loss_r) { float2 p = row_at(r1, st1, i); tp += pow(fabs((double)p.y - (double)p.x), (double)q); }
-        }
+#pragma unroll 4
+        for (int i = tid; i < n; i += nt) match1[i] = -1;
+        if (A.loss_r)
+            for (int i = tid; i < n; i += nt) { float2 p = row_at(r1, st1, i); tp += pow(fabs((double)p.y - (double)p.x), (double)q); }
         double total = block_sum(part, s_red);
         if (A.loss_r) tp = block_sum(tp, s_red);
 

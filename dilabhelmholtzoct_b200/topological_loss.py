@@ -122,6 +122,78 @@ def topo_loss(pred_obj, true_obj, lamda, interp=0, feat_d=2, loss_q=2, loss_r=Fa
     return _TopoLossFn.apply(pred, truth, lamda, feat_d, loss_q, loss_r, 0)
 
 
+_COPY_STREAMS = {}
+
+
+def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=2, loss_r=False, *,
+                        device=None, chunks=4, want_grad=True):
+    """``topo_loss`` for inputs that live in (pinned) HOST memory: forward + backward with the
+    host->device copies pipelined against the kernels.
+
+    The batch is cut into ``chunks`` groups of whole images; group i+1 is copied on a side stream
+    while group i runs ``tl_forward`` / ``tl_backward`` (with ``B_global = B`` so the partial losses
+    add up to ``lamda * mean_b W_b`` and gradients carry ``1/B``).  Returns ``(loss, grad_pred)``:
+    a 0-d device tensor and the ``[B, C, H, W]`` device gradient of the (resampled, if ``interp``)
+    prediction, or ``None`` when ``want_grad`` is false.  Same semantics as ``topo_loss(...)``
+    followed by ``.backward()``.
+    """
+    if lamda == 0.0:
+        return 0.0, None
+    if interp != 0:
+        raise ValueError("topo_loss_from_host takes maps at their final resolution (interp=0)")
+    if pred_host.shape != true_host.shape or pred_host.dim() != 4:
+        raise ValueError("expected two [B, C, H, W] tensors of the same shape")
+    if pred_host.dtype != torch.float32 or true_host.dtype != torch.float32:
+        raise ValueError("topo_loss expects float32 maps")
+    if feat_d not in (0, 1):
+        raise ValueError("feat_d must be 0 or 1 for 2-D maps (the reference call site uses feat_d=1)")
+    dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    B, C, H, W = pred_host.shape
+    if H < 2 or W < 2 or (B == 1 and C == 1):
+        raise ValueError("unsupported shape (see topo_loss)")
+    if B == 1:  # the reference's .squeeze() quirk: every channel is its own image
+        pred_host, true_host = pred_host.reshape(C, 1, H, W), true_host.reshape(C, 1, H, W)
+        B, C = C, 1
+    L = _lib.lib()
+    chunks = max(1, min(int(chunks), B))
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
+        side = _COPY_STREAMS.get(dev.index)
+        if side is None:
+            side = _COPY_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        pred = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+        truth = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+        grad = torch.empty((B, C, H, W), dtype=torch.float32, device=dev) if want_grad else None
+        parts = torch.empty((chunks,), dtype=torch.float32, device=dev)
+        bounds = [(i * B) // chunks for i in range(chunks + 1)]
+        events = []
+        with torch.cuda.stream(side):
+            for i in range(chunks):
+                a, b = bounds[i], bounds[i + 1]
+                pred[a:b].copy_(pred_host[a:b], non_blocking=True)
+                truth[a:b].copy_(true_host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                events.append(ev)
+        keep = []
+        for i in range(chunks):
+            a, b = bounds[i], bounds[i + 1]
+            cur.wait_event(events[i])
+            ws = _workspace(b - a, C, H, W, feat_d, dev)
+            keep.append(ws)
+            rc = L.tl_forward(pred[a:b].data_ptr(), truth[a:b].data_ptr(), b - a, C, H, W, feat_d, float(loss_q),
+                              float(lamda), int(bool(loss_r)), B, ws.data_ptr(), ws.numel(),
+                              parts[i:].data_ptr(), cur.cuda_stream)
+            _lib.check(rc, "tl_forward")
+            if want_grad:
+                rc = L.tl_backward(None, ws.data_ptr(), ws.numel(), b - a, C, H, W, feat_d, float(loss_q),
+                                   float(lamda), int(bool(loss_r)), B, grad[a:b].data_ptr(), cur.cuda_stream)
+                _lib.check(rc, "tl_backward")
+        loss = parts.sum()
+    return loss, grad
+
+
 # ---------------------------------------------------------------- inner boundaries (parity tests)
 
 def persistence_pairs(maps: torch.Tensor, dim: int) -> List[torch.Tensor]:

@@ -271,3 +271,16 @@ def test_forward_is_deterministic():
     for _ in range(3):
         b = _loss_and_grad(pred, truth, 0.1, feat_d=1)
         assert a[0] == b[0] and np.array_equal(a[1] != 0, b[1] != 0)
+
+
+def test_host_api_matches_autograd_path():
+    import dilabhelmholtzoct_b200 as tlb
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(6, 64, 64, seed=31, n_classes=3)
+    want_loss, want_grad = _loss_and_grad(pred, truth, 0.1, feat_d=1)
+    loss, grad = tlb.topo_loss_from_host(pred.pin_memory(), truth.pin_memory(), 0.1, feat_d=1, chunks=4)
+    assert abs(float(loss) - want_loss) <= REL * abs(want_loss)
+    assert np.abs(grad.cpu().numpy() - want_grad).max() <= REL * np.abs(want_grad).max()
+    loss2, none = tlb.topo_loss_from_host(pred.pin_memory(), truth.pin_memory(), 0.1, feat_d=0, chunks=2, want_grad=False)
+    want0, _ = _loss_and_grad(pred, truth, 0.1, feat_d=0)
+    assert none is None and abs(float(loss2) - want0) <= REL * abs(want0)
