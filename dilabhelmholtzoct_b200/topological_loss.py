@@ -147,7 +147,9 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
         raise ValueError("topo_loss expects float32 maps")
     if feat_d not in (0, 1):
         raise ValueError("feat_d must be 0 or 1 for 2-D maps (the reference call site uses feat_d=1)")
-    dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
     B, C, H, W = pred_host.shape
     if H < 2 or W < 2 or (B == 1 and C == 1):
         raise ValueError("unsupported shape (see topo_loss)")
