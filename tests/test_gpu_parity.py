@@ -284,3 +284,38 @@ def test_host_api_matches_autograd_path():
     loss2, none = tlb.topo_loss_from_host(pred.pin_memory(), truth.pin_memory(), 0.1, feat_d=0, chunks=2, want_grad=False)
     want0, _ = _loss_and_grad(pred, truth, 0.1, feat_d=0)
     assert none is None and abs(float(loss2) - want0) <= REL * abs(want0)
+
+
+def test_full_c2_batch_against_oracle():
+    """BASELINE configs[1] at full size: fp32[64,14,256,256], feat_d=1 -- loss, gradient support and
+    per-map pair counts against the (multi-threaded) oracle."""
+    import os
+    import dilabhelmholtzoct_b200 as tlb
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(64, 256, 256, seed=1234 + 2000)
+    loss, grad = _loss_and_grad(pred, truth, 0.1, feat_d=1)
+    want, wgrad, cnt = oracle.topo_loss(pred.numpy(), truth.numpy(), 0.1, feat_d=1, nthreads=os.cpu_count() or 1)
+    assert abs(loss - want) <= REL * abs(want), (loss, want)
+    assert np.array_equal(grad != 0, wgrad != 0)
+    assert np.abs(grad - wgrad).max() <= REL * np.abs(wgrad).max()
+    # size-independent property: every map's gradient entries sum to ~0 for diagonal-matched pairs
+    # (each contributes (-g/2, +g/2)); matched pairs break this only on maps with truth points
+    per_map = grad.reshape(64 * 14, -1).sum(1)
+    no_truth = cnt[:, 1] == 0
+    assert np.abs(per_map[no_truth]).max() <= 1e-3 * np.abs(grad).max()
+
+
+@pytest.mark.parametrize("dim", [0, 1])
+def test_pairs_1024(dim):
+    """BASELINE configs[4] resolution: one smooth-ish and one tie-heavy 1024x1024 map."""
+    rng = np.random.default_rng(9)
+    a = rng.random((1024, 1024)).astype(np.float32)
+    b = (np.round(rng.random((1024, 1024)) * 3) / 3).astype(np.float32)
+    _assert_same_pairs(np.stack([a, b]), dim)
+
+
+def test_loss_1024_small_batch():
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(1, 1024, 1024, seed=55, n_classes=3)
+    pred = torch.cat([pred, pred.flip(-1)]); truth = torch.cat([truth, truth.flip(-1)])
+    _check_loss(pred, truth, 0.1, 1)
