@@ -103,6 +103,95 @@ struct __align__(16) CrossEdge {
     uint32_t la, lb;
 };
 
+// dense edge id -> pixel that gudhi's coface walk reaches from that edge
+template <int DIM>
+__device__ __forceinline__ int edge_top_eid(const Geo<DIM>& g, uint32_t eid) {
+    const int RW = 2 * g.W + 1;
+    const int i = (int)eid / RW, rem = (int)eid - i * RW;
+    return rem < g.W ? g.hedge_top(i, rem) : g.vedge_top(i, rem - g.W);
+}
+
+// ---- packed triplet table: one 64-bit word per basin
+//   [ 32-bit ordered edge value | P-bit ordered dense edge id | G-bit target basin ],  P + G <= 32,
+// so the whole (value, position) edge key is in the word and every comparison is exact; updated
+// with ATOMS.CAS.64.  The basin's own root value sits in a separate array (read at decide time only).
+struct Packed {
+    uint32_t t_s, z_s;   // shared-window addresses of T64[] and zval[]
+    int G;               // bits of the target field
+    uint32_t gmask;
+};
+__device__ __forceinline__ uint64_t pk_load(uint32_t addr) {
+    uint64_t v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t pk_load32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool pk_cas(uint32_t addr, uint64_t expect, uint64_t want) {
+    uint64_t old;
+    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr), "l"(expect), "l"(want) : "memory");
+    return old == expect;
+}
+
+template <int DIM>
+__device__ __forceinline__ void merge_lanes_packed(const Packed& T, const CrossEdge* __restrict__ elist, int i, int i_end TL_SPARAM) {
+    const int G = T.G;
+    const uint64_t root_u = ~0ull >> G;       // upper part of a live basin's entry
+    const uint32_t lowmask = (1u << (32 - G)) - 1u;  // the ordered dense edge id fits 32 - G bits
+    uint32_t x = 0u, y = 0u;
+    uint64_t su = 0ull, ea = 0ull, eb = 0ull;
+    bool active = false, doneA = true, doneB = true;
+    CrossEdge nxt;
+    nxt.skey = 0ull; nxt.la = nxt.lb = 0u;
+    bool have_next = i < i_end;
+    if (have_next) nxt = elist[i];
+    for (;;) {
+        if (!active && have_next) {
+            x = nxt.la; y = nxt.lb;
+            // upper part of the word: [ordered value 32 | ordered edge id (32 - G bits)]
+            su = ((nxt.skey >> 32) << (32 - G)) | ((uint32_t)nxt.skey & lowmask);
+            doneA = doneB = false; active = true;
+            TL_STAT(1);
+            ++i;
+            have_next = i < i_end;
+            if (have_next) nxt = elist[i];
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        if (active) {
+            if (!doneA) { TL_STAT(0); ea = pk_load(T.t_s + x * 8u); }
+            if (!doneB) { TL_STAT(0); eb = pk_load(T.t_s + y * 8u); }
+            if (!doneA) { if ((ea >> G) > su) doneA = true; else x = (uint32_t)ea & T.gmask; }
+            if (!doneB) { if ((eb >> G) > su) doneB = true; else y = (uint32_t)eb & T.gmask; }
+            if (doneA && doneB) {
+                TL_STAT(2);
+                if (x == y) {
+                    active = false;
+                } else {
+                    TL_STAT(3);
+                    const uint32_t zx = pk_load32(T.z_s + x * 4u), zy = pk_load32(T.z_s + y * 4u);
+                    const bool sw = basin_elder<DIM>(y, zy, x, zx);
+                    const uint32_t xx = sw ? y : x, yy = sw ? x : y;  // yy: the younger representative
+                    const uint64_t ey = sw ? ea : eb;
+                    if (pk_cas(T.t_s + yy * 8u, ey, (su << G) | xx)) {
+                        if ((ey >> G) == root_u) {
+                            active = false;
+                        } else {  // re-assert yy's former connection for xx
+                            TL_STAT(4);
+                            x = xx; y = (uint32_t)ey & T.gmask; su = ey >> G; doneA = doneB = false;
+                        }
+                    } else {
+                        TL_STAT(5);
+                        x = xx; y = yy; doneA = doneB = false;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Lock-free Merge of the edges elist[i..i_end) of this lane, as a state machine executed in lock
 // step by the warp.  Per lane: (x, y) are the current nodes of the two walks, doneA/doneB tell
 // whether the representative at level skey has been reached (ea / eb hold its entry).
@@ -434,14 +523,27 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         TL_PROF(3);
 
         // ---- phase B: triplet merge tree over basins
+        // packed 64-bit entries when edge id + basin id fit 32 bits next to the 32-bit value (always
+        // exact); otherwise 128-bit entries, in shared memory if they fit, else in the global spill
+        const int n_edge_ids = H * GW + W;  // dense ids 0 .. H*(2W+1)+W-1
+        const int Pbits = 32 - __clz(n_edge_ids), Gbits = 32 - __clz(K + 1);
+        const bool packed = Pbits + Gbits <= 32 && (size_t)(K + 1) * 12 + 16 <= (size_t)kSmallSmemBytes;
         const bool t_in_smem = K + 1 <= t_cap_smem;
         TRef T;
         T.g = t_in_smem ? Ts : S.T2g + (size_t)blockIdx.x * S.k_stride;
         T.s = (uint32_t)__cvta_generic_to_shared(Ts);
-        for (int c = tid; c <= K; c += nt) {
-            TEntry e;
-            e.ekey = kRootKey; e.target = (uint32_t)c; e.zval = c ? zvalg[c] : 0u;
-            T.g[c] = e;
+        Packed PK;
+        PK.t_s = T.s; PK.z_s = T.s + (uint32_t)(((K + 1) * 8 + 15) & ~15); PK.G = Gbits; PK.gmask = (1u << Gbits) - 1u;
+        uint64_t* T64 = reinterpret_cast<uint64_t*>(smem);
+        uint32_t* Z32 = reinterpret_cast<uint32_t*>(smem + (((K + 1) * 8 + 15) & ~15));
+        if (packed) {
+            for (int c = tid; c <= K; c += nt) { T64[c] = (~0ull << Gbits) | (uint32_t)c; Z32[c] = c ? zvalg[c] : 0u; }
+        } else {
+            for (int c = tid; c <= K; c += nt) {
+                TEntry e;
+                e.ekey = kRootKey; e.target = (uint32_t)c; e.zval = c ? zvalg[c] : 0u;
+                T.g[c] = e;
+            }
         }
         __syncthreads();
         // pass 1 (streaming): compact the edges that cross two basins into a per-CTA list
@@ -476,20 +578,22 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 const int r = rr[u], c = cc[u];
 #pragma unroll
                 for (int k = 0; k < (DIM == 1 ? 4 : 2); ++k) {
-                    // k = 0: v-edge, k = 1: h-edge, k = 2 / 3: right / bottom boundary edges (H1 only)
+                    // k = 0: v-edge, k = 1: h-edge, k = 2 / 3: right / bottom boundary edges (H1 only).
+                    // `pos` is the DENSE edge id: rank of the edge among edges in bitmap order (row i of the
+                    // bitmap pair holds W h-edges then W+1 v-edges), order-isomorphic to the bitmap position
                     bool cross = false;
                     uint32_t lo = 0u, pos = 0u;
                     float val = 0.f;
                     if (valid) {
                         if (DIM == 1) {
-                            if (k == 0) { lo = lo1[u]; cross = lo != lab[u]; pos = (uint32_t)(2 * c + (2 * r + 1) * GW); }
-                            else if (k == 1) { lo = lo2[u]; cross = lo != lab[u]; pos = (uint32_t)(2 * c + 1 + (2 * r) * GW); }
-                            else if (k == 2) { cross = c == W - 1 && lab[u] != 0u; pos = (uint32_t)(2 * W + (2 * r + 1) * GW); }
-                            else { cross = r == H - 1 && lab[u] != 0u; pos = (uint32_t)(2 * c + 1 + (2 * H) * GW); }
+                            if (k == 0) { lo = lo1[u]; cross = lo != lab[u]; pos = (uint32_t)(r * GW + W + c); }
+                            else if (k == 1) { lo = lo2[u]; cross = lo != lab[u]; pos = (uint32_t)(r * GW + c); }
+                            else if (k == 2) { cross = c == W - 1 && lab[u] != 0u; pos = (uint32_t)(r * GW + 2 * W); }
+                            else { cross = r == H - 1 && lab[u] != 0u; pos = (uint32_t)(H * GW + c); }
                             if (cross) val = k == 0 ? g.vedge_val(r, c) : k == 1 ? g.hedge_val(r, c) : g.px(r, c);
                         } else {
-                            if (k == 0) { lo = lo1[u]; cross = lo != lab[u]; pos = (uint32_t)(2 * c + (2 * r + 1) * GW); if (cross) val = g.vedge_val(r, c); }
-                            else { lo = lo2[u]; cross = lo != lab[u]; pos = (uint32_t)(2 * c + 1 + (2 * r) * GW); if (cross) val = g.hedge_val(r, c); }
+                            if (k == 0) { lo = lo1[u]; cross = lo != lab[u]; pos = (uint32_t)(r * GW + W + c); if (cross) val = g.vedge_val(r, c); }
+                            else { lo = lo2[u]; cross = lo != lab[u]; pos = (uint32_t)(r * GW + c); if (cross) val = g.hedge_val(r, c); }
                         }
                     }
                     const unsigned bal = __ballot_sync(0xFFFFFFFFu, cross);
@@ -518,7 +622,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             const int per = (n_cross + nt - 1) / nt;
             int i = min(n_cross, tid * per);
             const int i_end = min(n_cross, i + per);
-            if (t_in_smem) merge_lanes<DIM, true>(T, elist, i, i_end TL_SARG);
+            if (packed) merge_lanes_packed<DIM>(PK, elist, i, i_end TL_SARG);
+            else if (t_in_smem) merge_lanes<DIM, true>(T, elist, i, i_end TL_SARG);
             else merge_lanes<DIM, false>(T, elist, i, i_end TL_SARG);
         }
 #ifdef TL_STATS
@@ -538,18 +643,33 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             PairRec rec;
             uint64_t sk = 0;
             if (c <= K) {
-                const TEntry e = t_in_smem ? t_load<true>(T, (uint32_t)c) : t_load<false>(T, (uint32_t)c);
+                TEntry e;
+                if (packed) {
+                    const uint64_t w = T64[c];
+                    const uint64_t up = w >> Gbits;  // [value 32 | ordered edge id]
+                    e.zval = Z32[c];
+                    if (up == (~0ull >> Gbits)) e.ekey = kRootKey;
+                    else {
+                        const uint32_t idk = (uint32_t)up & ((1u << (32 - Gbits)) - 1u);
+                        // restore the full-width ordered id (complemented for H1) used by the 128-bit form
+                        const uint32_t id32 = DIM == 1 ? ~(((1u << (32 - Gbits)) - 1u) - idk) : idk;
+                        e.ekey = ((up >> (32 - Gbits)) << 32) | id32;
+                    }
+                    e.target = 0u;
+                } else {
+                    e = t_in_smem ? t_load<true>(T, (uint32_t)c) : t_load<false>(T, (uint32_t)c);
+                }
                 const int x = (int)rootpix[c];
                 if (e.ekey != kRootKey) {
                     if ((uint32_t)(e.ekey >> 32) != e.zval) {
                         emit = true;
                         if (DIM == 1) {
-                            rec.cre = g.edge_top((uint32_t)(~e.ekey));
+                            rec.cre = edge_top_eid<DIM>(g, (uint32_t)(~e.ekey));
                             rec.des = x;
                             sk = ((uint64_t)(~e.zval) << 32) | (uint32_t)x;  // death cell = square x
                         } else {
                             g.vertex_val(x / VW, x % VW, &rec.cre);
-                            rec.des = g.edge_top((uint32_t)e.ekey);
+                            rec.des = edge_top_eid<DIM>(g, (uint32_t)e.ekey);
                             sk = e.ekey;  // death cell = edge
                         }
                     }
