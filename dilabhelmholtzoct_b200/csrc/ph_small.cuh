@@ -136,30 +136,64 @@ __device__ __forceinline__ bool pk_cas(uint32_t addr, uint64_t expect, uint64_t 
     return old == expect;
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int kRing = 64;  // edges per warp in the shared staging ring (two cp.async batches of 32)
+
+// Lock-free Merge of the warp's slice elist[beg..end) as a warp-synchronous state machine.
+// Edges are staged global -> shared with cp.async in coalesced batches of 32 (no register
+// scoreboard on the loads) and handed to whichever lanes are idle by ballot rank, so the warp's
+// lanes stay equally loaded.  Per iteration every active lane advances BOTH representative walks
+// by one hop (two independent 8-byte loads in flight).
 template <int DIM>
-__device__ __forceinline__ void merge_lanes_packed(const Packed& T, const CrossEdge* __restrict__ elist, int i, int i_end TL_SPARAM) {
+__device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossEdge* __restrict__ elist, int beg, int end,
+                                                   uint32_t ring_s TL_SPARAM) {
+    const int lane = threadIdx.x & 31;
     const int G = T.G;
-    const uint64_t root_u = ~0ull >> G;       // upper part of a live basin's entry
+    const uint64_t root_u = ~0ull >> G;              // upper part of a live basin's entry
     const uint32_t lowmask = (1u << (32 - G)) - 1u;  // the ordered dense edge id fits 32 - G bits
+    const int total = end - beg;
+    int cons = 0, avail = 0, issued = 0;
     uint32_t x = 0u, y = 0u;
     uint64_t su = 0ull, ea = 0ull, eb = 0ull;
     bool active = false, doneA = true, doneB = true;
-    CrossEdge nxt;
-    nxt.skey = 0ull; nxt.la = nxt.lb = 0u;
-    bool have_next = i < i_end;
-    if (have_next) nxt = elist[i];
+#define TL_ISSUE()                                                                              \
+    do {                                                                                        \
+        const int idx_ = issued + lane;                                                         \
+        if (idx_ < total) cp_async16(ring_s + (uint32_t)(idx_ & (kRing - 1)) * 16u, elist + beg + idx_); \
+        cp_async_commit();                                                                      \
+        issued = min(total, issued + 32);                                                       \
+    } while (0)
+    if (total > 0) TL_ISSUE();
+    if (issued < total) TL_ISSUE();
     for (;;) {
-        if (!active && have_next) {
-            x = nxt.la; y = nxt.lb;
-            // upper part of the word: [ordered value 32 | ordered edge id (32 - G bits)]
-            su = ((nxt.skey >> 32) << (32 - G)) | ((uint32_t)nxt.skey & lowmask);
-            doneA = doneB = false; active = true;
-            TL_STAT(1);
-            ++i;
-            have_next = i < i_end;
-            if (have_next) nxt = elist[i];
+        const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
+        if (need && cons < total) {
+            const int want = min(__popc(need), total - cons);
+            if (cons + want > avail) { cp_async_wait_all(); __syncwarp(); avail = issued; }
+            const int take = min(want, avail - cons);
+            const int rank = __popc(need & lanemask_lt());
+            if (!active && rank < take) {
+                const uint32_t a_ = ring_s + (uint32_t)((cons + rank) & (kRing - 1)) * 16u;
+                uint32_t k0, k1, la, lb;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(k0), "=r"(k1), "=r"(la), "=r"(lb) : "r"(a_) : "memory");
+                x = la; y = lb;
+                su = ((uint64_t)k1 << (32 - G)) | (k0 & lowmask);  // [ordered value 32 | ordered edge id]
+                doneA = doneB = false; active = true;
+                TL_STAT(1);
+            }
+            cons += take;
+            __syncwarp();  // ring slots read before they may be overwritten
+            while (issued < total && issued - cons <= kRing - 32) TL_ISSUE();
         }
-        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        if (!__any_sync(0xFFFFFFFFu, active)) {
+            if (cons >= total) break;
+            continue;
+        }
         if (active) {
             if (!doneA) { TL_STAT(0); ea = pk_load(T.t_s + x * 8u); }
             if (!doneB) { TL_STAT(0); eb = pk_load(T.t_s + y * 8u); }
@@ -190,6 +224,7 @@ __device__ __forceinline__ void merge_lanes_packed(const Packed& T, const CrossE
             }
         }
     }
+#undef TL_ISSUE
 }
 
 // Lock-free Merge of the edges elist[i..i_end) of this lane, as a state machine executed in lock
@@ -527,7 +562,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         // exact); otherwise 128-bit entries, in shared memory if they fit, else in the global spill
         const int n_edge_ids = H * GW + W;  // dense ids 0 .. H*(2W+1)+W-1
         const int Pbits = 32 - __clz(n_edge_ids), Gbits = 32 - __clz(K + 1);
-        const bool packed = Pbits + Gbits <= 32 && (size_t)(K + 1) * 12 + 16 <= (size_t)kSmallSmemBytes;
+        const size_t ring_off = (size_t)(((K + 1) * 8 + 15) & ~15) + (size_t)(((K + 1) * 4 + 15) & ~15);
+        const bool packed = Pbits + Gbits <= 32 && ring_off + (size_t)(kPhThreads / 32) * kRing * sizeof(CrossEdge) <= (size_t)kSmallSmemBytes;
         const bool t_in_smem = K + 1 <= t_cap_smem;
         TRef T;
         T.g = t_in_smem ? Ts : S.T2g + (size_t)blockIdx.x * S.k_stride;
@@ -619,12 +655,17 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         // differently long walks.
         {
             const int n_cross = s_ncross;
-            const int per = (n_cross + nt - 1) / nt;
-            int i = min(n_cross, tid * per);
-            const int i_end = min(n_cross, i + per);
-            if (packed) merge_lanes_packed<DIM>(PK, elist, i, i_end TL_SARG);
-            else if (t_in_smem) merge_lanes<DIM, true>(T, elist, i, i_end TL_SARG);
-            else merge_lanes<DIM, false>(T, elist, i, i_end TL_SARG);
+            if (packed) {  // contiguous slice per warp, edges handed to idle lanes
+                const int perw = (n_cross + (nt >> 5) - 1) / (nt >> 5);
+                const int wb = min(n_cross, warp * perw), we = min(n_cross, wb + perw);
+                merge_warpq_packed<DIM>(PK, elist, wb, we, T.s + (uint32_t)ring_off + (uint32_t)warp * kRing * 16u TL_SARG);
+            } else {       // contiguous chunk per lane
+                const int per = (n_cross + nt - 1) / nt;
+                int i = min(n_cross, tid * per);
+                const int i_end = min(n_cross, i + per);
+                if (t_in_smem) merge_lanes<DIM, true>(T, elist, i, i_end TL_SARG);
+                else merge_lanes<DIM, false>(T, elist, i, i_end TL_SARG);
+            }
         }
 #ifdef TL_STATS
         for (int i = 0; i < 8; ++i) if (g_stats_local[i]) { atomicAdd(&g_stats[i], (unsigned long long)g_stats_local[i]); g_stats_local[i] = 0; }
