@@ -386,13 +386,31 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         {
             unsigned long long best = 0ull;
             uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+            if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.f) & 15) == 0) {
+                const float4* f4 = reinterpret_cast<const float4*>(g.f);
 #pragma unroll 4
-            for (int p = tid; p < N; p += nt) {
-                const uint32_t m = mono32(__ldg(g.f + p));
-                lo = min(lo, m); hi = max(hi, m);
-                if (DIM == 0) {
-                    unsigned long long k = ((unsigned long long)m << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)p);
-                    best = k > best ? k : best;
+                for (int q = tid; q < (N >> 2); q += nt) {  // coalesced 128-bit loads
+                    const float4 v = __ldg(f4 + q);
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t m = mono32(vv[k]);
+                        lo = min(lo, m); hi = max(hi, m);
+                        if (DIM == 0) {
+                            unsigned long long kk = ((unsigned long long)m << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)(4 * q + k));
+                            best = kk > best ? kk : best;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 4
+                for (int p = tid; p < N; p += nt) {
+                    const uint32_t m = mono32(__ldg(g.f + p));
+                    lo = min(lo, m); hi = max(hi, m);
+                    if (DIM == 0) {
+                        unsigned long long k = ((unsigned long long)m << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)p);
+                        best = k > best ? k : best;
+                    }
                 }
             }
             lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
@@ -450,7 +468,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                         else if (fu >= fp) { other[u] = x - W; fo = fu; }
                         // else: strict local maximum, stays a root
                         // the far end is strictly higher (or OUTSIDE): its root is elder than x without any key lookup
-                        strict[u] = other[u] == (int)kOut16 || fo > fp;
+                        // (an equal far end with a larger raster index is elder too: whole plateaus take this path)
+                        strict[u] = other[u] == (int)kOut16 || fo > fp || (fo == fp && other[u] > x);
                         if (alias && other[u] == N - 1) { other[u] = (int)kOut16; strict[u] = true; }
                     } else {
                         uint64_t best = ~0ull;
@@ -607,47 +626,52 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     }
                 }
             }
+            // count this lane's crossing edges (at most 8 flags), ONE warp scan + ONE atomic per trip,
+            // then form and store the records
+            unsigned flags = 0u;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int x = x0 + u * nt + lane;
-                const bool valid = x < n_real;
+                if (x < n_real) {
+                    if (lo1[u] != lab[u]) flags |= 1u << (4 * u);
+                    if (lo2[u] != lab[u]) flags |= 2u << (4 * u);
+                    if (DIM == 1) {
+                        if (cc[u] == W - 1 && lab[u] != 0u) flags |= 4u << (4 * u);
+                        if (rr[u] == H - 1 && lab[u] != 0u) flags |= 8u << (4 * u);
+                    }
+                }
+            }
+            const int cnt = __popc(flags);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+            int slot = 0;
+            if (lane == 31 && incl > 0) slot = atomicAdd(&s_ncross, incl);
+            slot = __shfl_sync(0xFFFFFFFFu, slot, 31) + incl - cnt;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
                 const int r = rr[u], c = cc[u];
 #pragma unroll
                 for (int k = 0; k < (DIM == 1 ? 4 : 2); ++k) {
                     // k = 0: v-edge, k = 1: h-edge, k = 2 / 3: right / bottom boundary edges (H1 only).
                     // `pos` is the DENSE edge id: rank of the edge among edges in bitmap order (row i of the
                     // bitmap pair holds W h-edges then W+1 v-edges), order-isomorphic to the bitmap position
-                    bool cross = false;
-                    uint32_t lo = 0u, pos = 0u;
-                    float val = 0.f;
-                    if (valid) {
-                        if (DIM == 1) {
-                            if (k == 0) { lo = lo1[u]; cross = lo != lab[u]; pos = (uint32_t)(r * GW + W + c); }
-                            else if (k == 1) { lo = lo2[u]; cross = lo != lab[u]; pos = (uint32_t)(r * GW + c); }
-                            else if (k == 2) { cross = c == W - 1 && lab[u] != 0u; pos = (uint32_t)(r * GW + 2 * W); }
-                            else { cross = r == H - 1 && lab[u] != 0u; pos = (uint32_t)(H * GW + c); }
-                            if (cross) val = k == 0 ? g.vedge_val(r, c) : k == 1 ? g.hedge_val(r, c) : g.px(r, c);
-                        } else {
-                            if (k == 0) { lo = lo1[u]; cross = lo != lab[u]; pos = (uint32_t)(r * GW + W + c); if (cross) val = g.vedge_val(r, c); }
-                            else { lo = lo2[u]; cross = lo != lab[u]; pos = (uint32_t)(r * GW + c); if (cross) val = g.hedge_val(r, c); }
-                        }
-                    }
-                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, cross);
-                    if (bal) {
-                        int base = 0;
-                        const int leader = __ffs(bal) - 1;
-                        if (lane == leader) base = atomicAdd(&s_ncross, __popc(bal));
-                        base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                        if (cross) {
-                            CrossEdge ce;
-                            ce.skey = g.make_ekey(val, pos); ce.la = lo; ce.lb = lab[u];
-                            elist[base + __popc(bal & lanemask_lt())] = ce;
-                        }
+                    if (flags & (1u << (4 * u + k))) {
+                        uint32_t lo = 0u, pos;
+                        float val;
+                        if (k == 0) { lo = lo1[u]; pos = (uint32_t)(r * GW + W + c); val = g.vedge_val(r, c); }
+                        else if (k == 1) { lo = lo2[u]; pos = (uint32_t)(r * GW + c); val = g.hedge_val(r, c); }
+                        else if (k == 2) { pos = (uint32_t)(r * GW + 2 * W); val = g.px(r, c); }
+                        else { pos = (uint32_t)(H * GW + c); val = g.px(r, c); }
+                        CrossEdge ce;
+                        ce.skey = g.make_ekey(val, pos); ce.la = lo; ce.lb = lab[u];
+                        elist[slot++] = ce;
                     }
                 }
             }
         }
         __syncthreads();
+        TL_PROF(6);  // phase 4a: table init + crossing-edge compaction
         // pass 2: every lane owns a contiguous chunk of the list (all lanes have work; concurrently
         // processed edges are far apart -> few CAS conflicts).  The merge is a warp-synchronous state
         // machine: per iteration every active lane advances BOTH representative walks by one hop (two
@@ -674,61 +698,62 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         __syncthreads();
         TL_PROF(4);
 
-        // ---- emit
+        // ---- emit: every thread owns a contiguous run of basins, so ONE block scan yields
+        //      deterministic slots in basin (= raster) order
         PairRec* out = A.pairs[set] + (size_t)map * A.cap;
         uint64_t* skeys = A.skeys[set] ? A.skeys[set] + (size_t)map * A.cap : nullptr;
-        int emit_base = 0;
-        for (int c0 = 1; c0 <= K; c0 += nt) {
-            const int c = c0 + tid;
-            bool emit = false;
-            PairRec rec;
-            uint64_t sk = 0;
-            if (c <= K) {
-                TEntry e;
+        {
+            const int per = (K + nt - 1) / nt;  // <= 64 since K <= 65535
+            const int c_beg = 1 + tid * per, c_end = min(K + 1, c_beg + per);
+            auto load_entry = [&](int c, uint64_t& ekey, uint32_t& zv) {
                 if (packed) {
-                    const uint64_t w = T64[c];
-                    const uint64_t up = w >> Gbits;  // [value 32 | ordered edge id]
-                    e.zval = Z32[c];
-                    if (up == (~0ull >> Gbits)) e.ekey = kRootKey;
-                    else {
-                        const uint32_t idk = (uint32_t)up & ((1u << (32 - Gbits)) - 1u);
-                        // restore the full-width ordered id (complemented for H1) used by the 128-bit form
-                        const uint32_t id32 = DIM == 1 ? ~(((1u << (32 - Gbits)) - 1u) - idk) : idk;
-                        e.ekey = ((up >> (32 - Gbits)) << 32) | id32;
-                    }
-                    e.target = 0u;
+                    const uint64_t up = T64[c] >> Gbits;  // [value 32 | ordered edge id]
+                    zv = Z32[c];
+                    if (up == (~0ull >> Gbits)) { ekey = kRootKey; return; }
+                    const uint32_t lowmask = (1u << (32 - Gbits)) - 1u;
+                    const uint32_t idk = (uint32_t)up & lowmask;
+                    // restore the full-width ordered id (complemented for H1) used by the 128-bit form
+                    ekey = ((up >> (32 - Gbits)) << 32) | (DIM == 1 ? ~(lowmask - idk) : idk);
                 } else {
-                    e = t_in_smem ? t_load<true>(T, (uint32_t)c) : t_load<false>(T, (uint32_t)c);
+                    const TEntry e = t_in_smem ? t_load<true>(T, (uint32_t)c) : t_load<false>(T, (uint32_t)c);
+                    ekey = e.ekey; zv = e.zval;
                 }
+            };
+            unsigned long long flags = 0ull;
+            for (int c = c_beg; c < c_end; ++c) {
+                uint64_t ekey; uint32_t zv;
+                load_entry(c, ekey, zv);
+                const bool emit = ekey != kRootKey ? (uint32_t)(ekey >> 32) != zv : DIM == 0;  // essential class (H0)
+                if (emit) flags |= 1ull << (c - c_beg);
+            }
+            const int cnt = __popcll(flags);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+            if (lane == 31) s_wcnt[warp] = incl;
+            __syncthreads();
+            int slot = incl - cnt, total = 0;
+            for (int w = 0; w < kPhThreads / 32; ++w) { const int v = s_wcnt[w]; total += v; if (w < warp) slot += v; }
+            for (int c = c_beg; c < c_end; ++c) {
+                if (!((flags >> (c - c_beg)) & 1ull)) continue;
+                uint64_t ekey; uint32_t zv;
+                load_entry(c, ekey, zv);
                 const int x = (int)rootpix[c];
-                if (e.ekey != kRootKey) {
-                    if ((uint32_t)(e.ekey >> 32) != e.zval) {
-                        emit = true;
-                        if (DIM == 1) {
-                            rec.cre = edge_top_eid<DIM>(g, (uint32_t)(~e.ekey));
-                            rec.des = x;
-                            sk = ((uint64_t)(~e.zval) << 32) | (uint32_t)x;  // death cell = square x
-                        } else {
-                            g.vertex_val(x / VW, x % VW, &rec.cre);
-                            rec.des = edge_top_eid<DIM>(g, (uint32_t)e.ekey);
-                            sk = e.ekey;  // death cell = edge
-                        }
-                    }
-                } else if (DIM == 0) {  // essential class
-                    emit = true;
+                PairRec rec;
+                uint64_t sk;
+                if (ekey == kRootKey) {  // H0 essential class: paired with argmax, emitted last by gudhi
                     g.vertex_val(x / VW, x % VW, &rec.cre);
                     rec.des = (int)(0xFFFFFFFFu - (uint32_t)s_argmax);
                     sk = ~0ull;
+                } else if (DIM == 1) {
+                    rec.cre = edge_top_eid<DIM>(g, (uint32_t)(~ekey));
+                    rec.des = x;
+                    sk = ((uint64_t)(~zv) << 32) | (uint32_t)x;  // death cell = square x
+                } else {
+                    g.vertex_val(x / VW, x % VW, &rec.cre);
+                    rec.des = edge_top_eid<DIM>(g, (uint32_t)ekey);
+                    sk = ekey;  // death cell = edge
                 }
-            }
-            // deterministic slots: block-wide scan in basin (= raster) order, no atomics
-            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, emit);
-            if (lane == 0) s_wcnt[warp] = __popc(ballot);
-            __syncthreads();
-            int before = 0, total = 0;
-            for (int w = 0; w < kPhThreads / 32; ++w) { const int v = s_wcnt[w]; total += v; if (w < warp) before += v; }
-            if (emit) {
-                const int slot = emit_base + before + __popc(ballot & lanemask_lt());
                 if (slot < A.cap) {
                     rec.b = __ldg(g.f + rec.cre);
                     rec.d = __ldg(g.f + rec.des);
@@ -736,11 +761,10 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     out[slot] = rec;
                     if (skeys) skeys[slot] = sk;
                 }
+                ++slot;
             }
-            emit_base += total;
-            __syncthreads();
+            if (tid == 0) s_count = total;
         }
-        if (tid == 0) s_count = emit_base;
         __syncthreads();
         if (tid == 0) A.counts[set][map] = s_count;
         TL_PROF(5);
