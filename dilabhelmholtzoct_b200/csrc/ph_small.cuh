@@ -734,8 +734,14 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             __syncthreads();
             int slot = incl - cnt, total = 0;
             for (int w = 0; w < kPhThreads / 32; ++w) { const int v = s_wcnt[w]; total += v; if (w < warp) slot += v; }
-            for (int c = c_beg; c < c_end; ++c) {
-                if (!((flags >> (c - c_beg)) & 1ull)) continue;
+            // compact list of the emitting basins (zvalg is free after the table was initialised), then
+            // a coalesced pass: record j is formed by thread j mod 1024 and written to slot j
+            for (int c = c_beg; c < c_end; ++c)
+                if ((flags >> (c - c_beg)) & 1ull) zvalg[slot++] = (uint32_t)c;
+            __syncthreads();
+#pragma unroll 2
+            for (int j = tid; j < total; j += nt) {
+                const int c = (int)zvalg[j];
                 uint64_t ekey; uint32_t zv;
                 load_entry(c, ekey, zv);
                 const int x = (int)rootpix[c];
@@ -754,14 +760,13 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     rec.des = edge_top_eid<DIM>(g, (uint32_t)ekey);
                     sk = ekey;  // death cell = edge
                 }
-                if (slot < A.cap) {
+                if (j < A.cap) {
                     rec.b = __ldg(g.f + rec.cre);
                     rec.d = __ldg(g.f + rec.des);
                     rec.tb = rec.td = __int_as_float(0x7FC00000);
-                    out[slot] = rec;
-                    if (skeys) skeys[slot] = sk;
+                    out[j] = rec;
+                    if (skeys) skeys[j] = sk;
                 }
-                ++slot;
             }
             if (tid == 0) s_count = total;
         }
