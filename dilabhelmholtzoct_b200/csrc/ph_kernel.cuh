@@ -148,10 +148,12 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
 
         // ---- phase 1: level-0 contraction along each node's earliest incident edge
         const int n_real = DIM == 1 ? N : NN;
-        for (int x = tid; x < n_real; x += nt) {
+        const int n_real_pad = (n_real + 31) & ~31;
+        for (int x = tid; x < n_real_pad; x += nt) {  // warp-uniform trip count
             uint64_t best = ~0ull;
             int other = -1;
-            if (DIM == 1) {
+            if (x >= n_real) {
+            } else if (DIM == 1) {
                 const int r = x / W, c = x - r * W;
                 const float fp = g.px(r, c);
                 // top, bottom: h-edges; left, right: v-edges
@@ -197,6 +199,7 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
                 // a vertex always has an incident edge of its own value (min of the same pixels)
             }
             if (other >= 0) ph.union0(x, other);
+            __syncwarp();  // reconverge (independent thread scheduling lets the lanes drift apart otherwise)
         }
         __syncthreads();
         // flatten level-0 chains so that later finds are one hop
@@ -208,7 +211,9 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
 
         // ---- phase 2: all edges into the triplet merge tree
         const int n_vedges = H * (W + 1), n_hedges = (H + 1) * W;
-        for (int e = tid; e < n_vedges + n_hedges; e += nt) {
+        const int n_edges_pad = (n_vedges + n_hedges + 31) & ~31;
+        for (int e = tid; e < n_edges_pad; e += nt) {  // warp-uniform trip count
+            if (e >= n_vedges + n_hedges) { __syncwarp(); continue; }
             int a, b;
             uint32_t pos;
             float val;
@@ -229,8 +234,8 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
             uint64_t ta = ld_cg_u64(T + a), tb = ld_cg_u64(T + b);
             int la = (uint32_t)(ta >> 32) == kCodeL0 ? (int)(uint32_t)ta : a;
             int lb = (uint32_t)(tb >> 32) == kCodeL0 ? (int)(uint32_t)tb : b;
-            if (la == lb) continue;
-            ph.merge(la, lb, pos, g.make_ekey(val, pos));
+            if (la != lb) ph.merge(la, lb, pos, g.make_ekey(val, pos));
+            __syncwarp();
         }
         __syncthreads();
 
