@@ -739,33 +739,52 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             for (int c = c_beg; c < c_end; ++c)
                 if ((flags >> (c - c_beg)) & 1ull) zvalg[slot++] = (uint32_t)c;
             __syncthreads();
-#pragma unroll 2
-            for (int j = tid; j < total; j += nt) {
-                const int c = (int)zvalg[j];
-                uint64_t ekey; uint32_t zv;
-                load_entry(c, ekey, zv);
-                const int x = (int)rootpix[c];
-                PairRec rec;
-                uint64_t sk;
-                if (ekey == kRootKey) {  // H0 essential class: paired with argmax, emitted last by gudhi
-                    g.vertex_val(x / VW, x % VW, &rec.cre);
-                    rec.des = (int)(0xFFFFFFFFu - (uint32_t)s_argmax);
-                    sk = ~0ull;
-                } else if (DIM == 1) {
-                    rec.cre = edge_top_eid<DIM>(g, (uint32_t)(~ekey));
-                    rec.des = x;
-                    sk = ((uint64_t)(~zv) << 32) | (uint32_t)x;  // death cell = square x
-                } else {
-                    g.vertex_val(x / VW, x % VW, &rec.cre);
-                    rec.des = edge_top_eid<DIM>(g, (uint32_t)ekey);
-                    sk = ekey;  // death cell = edge
+            // 4 records per thread per trip, staged so that the dependent global loads
+            // (basin id -> root pixel -> map values) of the 4 records overlap
+            for (int j0 = tid; j0 < total; j0 += 4 * nt) {
+                int cc4[4], xx4[4];
+                uint64_t ek4[4];
+                uint32_t zv4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int j = j0 + u * nt; cc4[u] = j < total ? (int)zvalg[j] : 0; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * nt;
+                    xx4[u] = 0; ek4[u] = kRootKey; zv4[u] = 0u;
+                    if (j < total) { xx4[u] = (int)rootpix[cc4[u]]; load_entry(cc4[u], ek4[u], zv4[u]); }
                 }
-                if (j < A.cap) {
-                    rec.b = __ldg(g.f + rec.cre);
-                    rec.d = __ldg(g.f + rec.des);
-                    rec.tb = rec.td = __int_as_float(0x7FC00000);
-                    out[j] = rec;
-                    if (skeys) skeys[j] = sk;
+                PairRec rec4[4];
+                uint64_t sk4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * nt;
+                    rec4[u].cre = rec4[u].des = 0; sk4[u] = 0ull;
+                    if (j >= total) continue;
+                    const int x = xx4[u];
+                    if (ek4[u] == kRootKey) {  // H0 essential class: paired with argmax, emitted last by gudhi
+                        g.vertex_val(x / VW, x % VW, &rec4[u].cre);
+                        rec4[u].des = (int)(0xFFFFFFFFu - (uint32_t)s_argmax);
+                        sk4[u] = ~0ull;
+                    } else if (DIM == 1) {
+                        rec4[u].cre = edge_top_eid<DIM>(g, (uint32_t)(~ek4[u]));
+                        rec4[u].des = x;
+                        sk4[u] = ((uint64_t)(~zv4[u]) << 32) | (uint32_t)x;  // death cell = square x
+                    } else {
+                        g.vertex_val(x / VW, x % VW, &rec4[u].cre);
+                        rec4[u].des = edge_top_eid<DIM>(g, (uint32_t)ek4[u]);
+                        sk4[u] = ek4[u];  // death cell = edge
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * nt;
+                    if (j < total && j < A.cap) {
+                        rec4[u].b = __ldg(g.f + rec4[u].cre);
+                        rec4[u].d = __ldg(g.f + rec4[u].des);
+                        rec4[u].tb = rec4[u].td = __int_as_float(0x7FC00000);
+                        out[j] = rec4[u];
+                        if (skeys) skeys[j] = sk4[u];
+                    }
                 }
             }
             if (tid == 0) s_count = total;
