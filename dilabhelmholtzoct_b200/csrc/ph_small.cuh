@@ -4,7 +4,7 @@
 //
 //   phase A  level-0 union-find on 16-bit parents        par[65536]            (128 KB)
 //   census   basin roots get dense ids in raster order   root mask             (  8 KB)
-//            -> per-pixel basin id B[] (global, streamed), root pixel / root value per basin
+//            -> per-node basin id written in place into par[], root pixel / root value per basin
 //   phase B  triplet table over BASINS only, 16-byte self-contained entries
 //            {edge key 64, elder target 32, own root value 32}, updated with ATOMS.CAS.128
 //            (reuses phase A's shared memory; K <= ~14.5k basins fit, else global fallback)
@@ -288,11 +288,10 @@ struct PhSmallArgs {
     PhArgs base;
     CrossEdge* elist;    // [grid][e_stride] edges that cross two basins
     size_t e_stride;
-    uint16_t* Bg;        // [grid][b_stride] basin id per node
     uint32_t* rootpix;   // [grid][k_stride] root node of each basin
     uint32_t* zval;      // [grid][k_stride]
     TEntry* T2g;         // [grid][k_stride] fallback triplet table
-    size_t b_stride, k_stride;
+    size_t k_stride;
     unsigned long long* prof;  // optional [8] phase cycle counters
 };
 
@@ -354,7 +353,6 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
     uint32_t* mask = reinterpret_cast<uint32_t*>(smem + kParBytes);
     TEntry* Ts = reinterpret_cast<TEntry*>(smem);
     const int t_cap_smem = kSmallSmemBytes / (int)sizeof(TEntry);
-    uint16_t* Bg = S.Bg + (size_t)blockIdx.x * S.b_stride;
     uint32_t* rootpix = S.rootpix + (size_t)blockIdx.x * S.k_stride;
     uint32_t* zvalg = S.zval + (size_t)blockIdx.x * S.k_stride;
     const unsigned int n_jobs = (unsigned)A.n_sets * (unsigned)A.n_maps;
@@ -571,7 +569,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 const uint32_t r = par[x];
                 b = (DIM == 1 && r == kOut16) ? 0u : par[r];
             }
-            Bg[x] = (uint16_t)b;
+            par[x] = (uint16_t)b;  // in place: after the flatten nobody reads a non-root entry, roots keep their id
         }
         __syncthreads();
         TL_PROF(3);
@@ -591,16 +589,6 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         PK.t_s = T.s; PK.z_s = T.s + (uint32_t)(((K + 1) * 8 + 15) & ~15); PK.G = Gbits; PK.gmask = (1u << Gbits) - 1u;
         uint64_t* T64 = reinterpret_cast<uint64_t*>(smem);
         uint32_t* Z32 = reinterpret_cast<uint32_t*>(smem + (((K + 1) * 8 + 15) & ~15));
-        if (packed) {
-            for (int c = tid; c <= K; c += nt) { T64[c] = (~0ull << Gbits) | (uint32_t)c; Z32[c] = c ? zvalg[c] : 0u; }
-        } else {
-            for (int c = tid; c <= K; c += nt) {
-                TEntry e;
-                e.ekey = kRootKey; e.target = (uint32_t)c; e.zval = c ? zvalg[c] : 0u;
-                T.g[c] = e;
-            }
-        }
-        __syncthreads();
         // pass 1 (streaming): compact the edges that cross two basins into a per-CTA list
         CrossEdge* elist = S.elist + (size_t)blockIdx.x * S.e_stride;
         // every node owns its left/top edge (H1: pixel) or down/right edge (H0: vertex); the last
@@ -615,14 +603,14 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 if (x < n_real) {
                     if (DIM == 1) {
                         rr[u] = (int)divW.div((uint32_t)x); cc[u] = x - rr[u] * W;
-                        lab[u] = Bg[x];
-                        lo1[u] = cc[u] == 0 ? 0u : Bg[x - 1];   // across the left v-edge
-                        lo2[u] = rr[u] == 0 ? 0u : Bg[x - W];   // across the top h-edge
+                        lab[u] = par[x];
+                        lo1[u] = cc[u] == 0 ? 0u : par[x - 1];   // across the left v-edge
+                        lo2[u] = rr[u] == 0 ? 0u : par[x - W];   // across the top h-edge
                     } else {
                         rr[u] = (int)divVW.div((uint32_t)x); cc[u] = x - rr[u] * VW;
-                        lab[u] = Bg[x];
-                        lo1[u] = rr[u] < H ? Bg[x + VW] : lab[u];  // down v-edge
-                        lo2[u] = cc[u] < W ? Bg[x + 1] : lab[u];   // right h-edge
+                        lab[u] = par[x];
+                        lo1[u] = rr[u] < H ? par[x + VW] : lab[u];  // down v-edge
+                        lo2[u] = cc[u] < W ? par[x + 1] : lab[u];   // right h-edge
                     }
                 }
             }
@@ -670,8 +658,18 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 }
             }
         }
+        __syncthreads();  // every basin id has been read: the union-find storage can become the table
+        if (packed) {
+            for (int c = tid; c <= K; c += nt) { T64[c] = (~0ull << Gbits) | (uint32_t)c; Z32[c] = c ? zvalg[c] : 0u; }
+        } else {
+            for (int c = tid; c <= K; c += nt) {
+                TEntry e;
+                e.ekey = kRootKey; e.target = (uint32_t)c; e.zval = c ? zvalg[c] : 0u;
+                T.g[c] = e;
+            }
+        }
         __syncthreads();
-        TL_PROF(6);  // phase 4a: table init + crossing-edge compaction
+        TL_PROF(6);  // phase 4a: crossing-edge compaction + table init
         // pass 2: every lane owns a contiguous chunk of the list (all lanes have work; concurrently
         // processed edges are far apart -> few CAS conflicts).  The merge is a warp-synchronous state
         // machine: per iteration every active lane advances BOTH representative walks by one hop (two

@@ -73,7 +73,7 @@ struct Layout {
     size_t counter, counts[2], cost, tpers, coef, pairs[2], skeys[2], match1;
     size_t T, t_stride;
     int small;  // 1: shared-memory persistence kernel (<= 65535 nodes)
-    size_t Bg, b_stride, rootpix, zval, T2g, k_stride, elist, e_stride;
+    size_t rootpix, zval, T2g, k_stride, elist, e_stride;
     size_t key_tmp, idx_a, idx_b, rec_tmp;
     size_t v, minv, u, way, pcol, used, stride_c, stride_r;
     size_t total;
@@ -98,9 +98,7 @@ Layout make_layout(int M, int H, int W, int dim, int B) {
     L.match1 = take(sizeof(int32_t) * (size_t)M * L.cap);
     L.small = dim == 1 ? ((long long)H * W <= 65536) : (L.n_nodes <= tl::kSmallMaxNodes);
     if (L.small) {
-        L.b_stride = align_up(sizeof(uint16_t) * (size_t)L.n_nodes) / sizeof(uint16_t);
         L.k_stride = align_up((size_t)L.cap + 2, 64);
-        L.Bg = take(sizeof(uint16_t) * L.b_stride * kSmallSlots);
         L.rootpix = take(sizeof(uint32_t) * L.k_stride * kSmallSlots);
         L.zval = take(sizeof(uint32_t) * L.k_stride * kSmallSlots);
         L.T2g = take(sizeof(tl::TEntry) * L.k_stride * kSmallSlots);
@@ -165,9 +163,9 @@ int launch_ph(const float* m0, const float* m1, int n_sets, const Layout& L, int
         if (grid > kSmallSlots) grid = kSmallSlots;
         tl::PhSmallArgs sa;
         sa.base = a;
-        sa.Bg = at<uint16_t>(ws, L.Bg); sa.rootpix = at<uint32_t>(ws, L.rootpix); sa.zval = at<uint32_t>(ws, L.zval);
+        sa.rootpix = at<uint32_t>(ws, L.rootpix); sa.zval = at<uint32_t>(ws, L.zval);
         sa.T2g = at<tl::TEntry>(ws, L.T2g);
-        sa.b_stride = L.b_stride; sa.k_stride = L.k_stride;
+        sa.k_stride = L.k_stride;
         sa.elist = at<tl::CrossEdge>(ws, L.elist); sa.e_stride = L.e_stride;
         const char* pe = getenv("TL_PROFILE");
         sa.prof = (pe && pe[0] == '1') ? at<unsigned long long>(ws, L.counter) + 8 : nullptr;
