@@ -198,16 +198,39 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
                 }
                 // a vertex always has an incident edge of its own value (min of the same pixels)
             }
-            if (other >= 0) ph.union0(x, other);
+            if (other >= 0) {
+                bool linked = false;
+                if (DIM == 1) {
+                    // far end strictly higher, or equal with a larger raster index, or OUTSIDE: it and all its
+                    // ancestors are elder than x, so x (still a root) links under its root without key lookups
+                    bool elder_far = other == g.OUT;
+                    if (!elder_far) {
+                        const float fp = __ldg(g.f + x), fo = __ldg(g.f + other);
+                        elder_far = fo > fp || (fo == fp && other > x);
+                    }
+                    if (elder_far) {
+                        const int rb = ph.find0(other);
+                        const unsigned long long expect = ((unsigned long long)kCodeRoot << 32) | (uint32_t)x;
+                        const unsigned long long want = ((unsigned long long)kCodeL0 << 32) | (uint32_t)rb;
+                        linked = atomicCAS(reinterpret_cast<unsigned long long*>(T + x), expect, want) == expect;
+                    }
+                }
+                if (!linked) ph.union0(x, other);
+            }
             __syncwarp();  // reconverge (independent thread scheduling lets the lanes drift apart otherwise)
         }
         __syncthreads();
-        // flatten level-0 chains so that later finds are one hop
-        for (int x = tid; x < n_real; x += nt) {
-            int r = ph.find0_ro(x);
-            if (r != x) T[x] = ((uint64_t)kCodeL0 << 32) | (uint32_t)r;
+        // flatten level-0 chains by pointer jumping (own entry only; depth halves per round)
+        for (;;) {
+            int changed = 0;
+            for (int x = tid; x < n_real; x += nt) {
+                const uint64_t t = ld_cg_u64(T + x);
+                if ((uint32_t)(t >> 32) != kCodeL0) continue;
+                const uint64_t tp = ld_cg_u64(T + (uint32_t)t);
+                if ((uint32_t)(tp >> 32) == kCodeL0) { T[x] = tp; changed = 1; }
+            }
+            if (!__syncthreads_or(changed)) break;
         }
-        __syncthreads();
 
         // ---- phase 2: all edges into the triplet merge tree
         const int n_vedges = H * (W + 1), n_hedges = (H + 1) * W;
