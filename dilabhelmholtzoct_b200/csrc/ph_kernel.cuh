@@ -16,6 +16,26 @@
 //
 // All comparisons use the exact cell order (value, bitmap position), so persistence pairs and
 // critical pixels are bit-exact under ties.
+//
+// Why the lock-free Merge is exact (tests/test_algorithm_model.py is the executable version):
+//   * Read every entry T[y] = (s, x) as the FACT "y and x are connected at level s", x elder than y.
+//     Facts are monotone in the level: true at s implies true at every later level.
+//   * Merge(a, s, b) first walks both sides to their representatives at level s, using only recorded
+//     facts with level <= s.  A stale read is harmless: an entry is only ever replaced by a fact with an
+//     EARLIER level for the same node, and the replaced fact is re-asserted by the replacing thread, so
+//     everything a thread has read stays true.
+//   * The single write is a CAS on the younger representative y: (s_old, x_old) -> (s, x) with s < s_old,
+//     after which the same thread continues with Merge(x, s_old, x_old).  Old fact + pending edge and new
+//     fact + pending re-assertion have the same closure, so the set of derivable connectivity facts is an
+//     invariant of every atomic step; at quiescence it equals the closure of all edges.
+//   * Every link points to a strictly elder node, so the pointer graph is acyclic and walks terminate;
+//     each successful CAS strictly lowers one entry's level, so the whole process terminates.
+//   * At quiescence each T[y].s is y's true death level: if y were connected to an elder node earlier
+//     than s, that connection would have to be derivable from facts of level < s, but those only join y
+//     to nodes hanging BELOW y (younger), because y's own link has level s.
+//   * Level-0 contraction is exact because forest paths are key-monotone towards the basin root: when a
+//     crossing edge is scanned, both its ends are already joined to their basin's core, and a basin root
+//     whose value exceeds the edge's value is already the eldest node of everything joined to it.
 #pragma once
 #include "tl_common.cuh"
 
