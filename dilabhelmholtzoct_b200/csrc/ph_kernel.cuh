@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
         __syncthreads();
         const unsigned int job = s_job;
         if (job >= n_jobs) break;
-        const int set = (int)(job % (unsigned)A.n_sets), map = (int)(job / (unsigned)A.n_sets);
+        // all prediction maps first (heavy), ground-truth maps (light) fill the tail of the launch
+        const int set = (int)(job / (unsigned)A.n_maps), map = (int)(job % (unsigned)A.n_maps);
         Ph<DIM> ph(A.maps[set] + (size_t)map * N, H, W, T);
         const Geo<DIM>& g = ph.g;
         const int NN = g.NN, GW = g.GW, VW = g.VW;

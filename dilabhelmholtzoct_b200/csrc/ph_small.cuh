@@ -171,8 +171,10 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
     if (total > 0) TL_ISSUE();
     if (issued < total) TL_ISSUE();
     for (;;) {
+        // refill in batches: hand out new edges only when a quarter of the lanes is idle (or all are),
+        // so the ~45-instruction refill section is not paid on every hop
         const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
-        if (need && cons < total) {
+        if ((__popc(need) >= 8 || need == 0xFFFFFFFFu) && cons < total) {
             const int want = min(__popc(need), total - cons);
             if (cons + want > avail) { cp_async_wait_all(); __syncwarp(); avail = issued; }
             const int take = min(want, avail - cons);
@@ -372,7 +374,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         const unsigned int job = s_job;
         if (job >= n_jobs) break;
         if (S.prof && tid == 0) t0 = clock64();
-        const int set = (int)(job % (unsigned)A.n_sets), map = (int)(job / (unsigned)A.n_sets);
+        // all prediction maps first (heavy), ground-truth maps (light) fill the tail of the launch
+        const int set = (int)(job / (unsigned)A.n_maps), map = (int)(job % (unsigned)A.n_maps);
         SmallCtx<DIM> cx(A.maps[set] + (size_t)map * N, H, W, par);
         const Geo<DIM>& g = cx.g;
         const int NN = g.NN, GW = g.GW, VW = g.VW;
