@@ -439,71 +439,84 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         // ---- phase 1: level-0 union-find in shared memory
         const bool alias = DIM == 1 && N == 65536;  // last pixel == OUTSIDE
         const FastDiv divW((uint32_t)W), divVW((uint32_t)VW), divW1((uint32_t)(W + 1));
-        // 4 nodes per lane per trip: the 4 x 5 map loads are in flight together (the loop is
-        // latency-bound otherwise); the unions follow, in shared memory
+        // pick(x): far end of x's earliest incident edge when that edge has x's own value (else -1), and
+        // whether that far end is known to be ELDER than x from registers alone
+        auto pick = [&](int x, int& oth, bool& elder_far) {
+            oth = -1; elder_far = false;
+            if (DIM == 1) {
+                const int r = (int)divW.div((uint32_t)x), c = x - r * W;
+                const float fp = g.px(r, c);
+                const float fu = r == 0 ? fp : g.px(r - 1, c), fd = r == H - 1 ? fp : g.px(r + 1, c);
+                const float fl = c == 0 ? fp : g.px(r, c - 1), fr = c == W - 1 ? fp : g.px(r, c + 1);
+                // earliest incident edge in the descending scan = largest (value, position): the
+                // value is fp whenever the far pixel is >= fp (or the edge is a boundary edge), and
+                // among those the bitmap position orders bottom > right > left > top
+                float fo = fp;
+                if (r == H - 1) oth = (int)kOut16;
+                else if (fd >= fp) { oth = x + W; fo = fd; }
+                else if (c == W - 1) oth = (int)kOut16;
+                else if (fr >= fp) { oth = x + 1; fo = fr; }
+                else if (c == 0) oth = (int)kOut16;
+                else if (fl >= fp) { oth = x - 1; fo = fl; }
+                else if (r == 0) oth = (int)kOut16;
+                else if (fu >= fp) { oth = x - W; fo = fu; }
+                // else: strict local maximum, stays a root
+                // strictly higher, OUTSIDE, or equal with a larger raster index: elder than x
+                elder_far = oth == (int)kOut16 || fo > fp || (fo == fp && oth > x);
+                if (alias && oth == N - 1) { oth = (int)kOut16; elder_far = true; }
+            } else {
+                uint64_t best = ~0ull;
+                const int i = (int)divVW.div((uint32_t)x), j = x - i * VW;
+                if (i > 0) {
+                    uint64_t k = g.make_ekey(g.vedge_val(i - 1, j), (uint32_t)(2 * j + (2 * i - 1) * GW));
+                    if (k < best) { best = k; oth = x - VW; }
+                }
+                if (i < H) {
+                    uint64_t k = g.make_ekey(g.vedge_val(i, j), (uint32_t)(2 * j + (2 * i + 1) * GW));
+                    if (k < best) { best = k; oth = x + VW; }
+                }
+                if (j > 0) {
+                    uint64_t k = g.make_ekey(g.hedge_val(i, j - 1), (uint32_t)(2 * j - 1 + (2 * i) * GW));
+                    if (k < best) { best = k; oth = x - 1; }
+                }
+                if (j < W) {
+                    uint64_t k = g.make_ekey(g.hedge_val(i, j), (uint32_t)(2 * j + 1 + (2 * i) * GW));
+                    if (k < best) { best = k; oth = x + 1; }
+                }
+            }
+        };
+        // phase 1a: a node whose far end is elder by registers just POINTS at it -- a plain store to
+        // its own entry, no atomics, no find (every entry has one writer in this phase).  The others
+        // (ties towards a smaller raster index; every H0 vertex) are flagged for phase 1b.
+        // 4 nodes per lane per trip so that the 4 x 5 map loads are in flight together.
         for (int x0 = warp * 32; x0 < n_real; x0 += 4 * nt) {  // warp-uniform trip count
             int other[4];
-            bool strict[4];
+            bool elder_far[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int x = x0 + u * nt + lane;
-                other[u] = -1;
-                strict[u] = false;
-                if (x < n_real && !(alias && x == N - 1)) {
-                    if (DIM == 1) {
-                        const int r = (int)divW.div((uint32_t)x), c = x - r * W;
-                        const float fp = g.px(r, c);
-                        const float fu = r == 0 ? fp : g.px(r - 1, c), fd = r == H - 1 ? fp : g.px(r + 1, c);
-                        const float fl = c == 0 ? fp : g.px(r, c - 1), fr = c == W - 1 ? fp : g.px(r, c + 1);
-                        // earliest incident edge in the descending scan = largest (value, position): the
-                        // value is fp whenever the far pixel is >= fp (or the edge is a boundary edge), and
-                        // among those the bitmap position orders bottom > right > left > top
-                        float fo = fp;
-                        if (r == H - 1) other[u] = (int)kOut16;
-                        else if (fd >= fp) { other[u] = x + W; fo = fd; }
-                        else if (c == W - 1) other[u] = (int)kOut16;
-                        else if (fr >= fp) { other[u] = x + 1; fo = fr; }
-                        else if (c == 0) other[u] = (int)kOut16;
-                        else if (fl >= fp) { other[u] = x - 1; fo = fl; }
-                        else if (r == 0) other[u] = (int)kOut16;
-                        else if (fu >= fp) { other[u] = x - W; fo = fu; }
-                        // else: strict local maximum, stays a root
-                        // the far end is strictly higher (or OUTSIDE): its root is elder than x without any key lookup
-                        // (an equal far end with a larger raster index is elder too: whole plateaus take this path)
-                        strict[u] = other[u] == (int)kOut16 || fo > fp || (fo == fp && other[u] > x);
-                        if (alias && other[u] == N - 1) { other[u] = (int)kOut16; strict[u] = true; }
-                    } else {
-                        uint64_t best = ~0ull;
-                        const int i = (int)divVW.div((uint32_t)x), j = x - i * VW;
-                        if (i > 0) {
-                            uint64_t k = g.make_ekey(g.vedge_val(i - 1, j), (uint32_t)(2 * j + (2 * i - 1) * GW));
-                            if (k < best) { best = k; other[u] = x - VW; }
-                        }
-                        if (i < H) {
-                            uint64_t k = g.make_ekey(g.vedge_val(i, j), (uint32_t)(2 * j + (2 * i + 1) * GW));
-                            if (k < best) { best = k; other[u] = x + VW; }
-                        }
-                        if (j > 0) {
-                            uint64_t k = g.make_ekey(g.hedge_val(i, j - 1), (uint32_t)(2 * j - 1 + (2 * i) * GW));
-                            if (k < best) { best = k; other[u] = x - 1; }
-                        }
-                        if (j < W) {
-                            uint64_t k = g.make_ekey(g.hedge_val(i, j), (uint32_t)(2 * j + 1 + (2 * i) * GW));
-                            if (k < best) { best = k; other[u] = x + 1; }
-                        }
-                    }
-                }
+                other[u] = -1; elder_far[u] = false;
+                if (x < n_real && !(alias && x == N - 1)) pick(x, other[u], elder_far[u]);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int x = x0 + u * nt + lane;
-                if (other[u] >= 0) {
-                    bool linked = false;
-                    if (strict[u]) {  // x is still a root and every ancestor of `other` is elder than x
-                        const uint32_t rb = cx.find((uint32_t)other[u]);
-                        linked = atomicCAS(reinterpret_cast<unsigned short*>(par + x), (unsigned short)x, (unsigned short)rb) == (unsigned short)x;
-                    }
-                    if (!linked) cx.union0((uint32_t)x, (uint32_t)other[u]);
+                const bool direct = other[u] >= 0 && elder_far[u];
+                if (direct) par[x] = (uint16_t)other[u];
+                const unsigned deferred = __ballot_sync(0xFFFFFFFFu, other[u] >= 0 && !direct);
+                if (lane == 0 && x0 + u * nt < n_real) mask[(x0 + u * nt) >> 5] = deferred;
+            }
+        }
+        __syncthreads();
+        // phase 1b: elder-linked lock-free unions (CAS on the younger root) for the flagged nodes
+        for (int w0 = warp; w0 < ((n_real + 31) >> 5); w0 += nt >> 5) {
+            const unsigned bits = mask[w0];
+            if (bits) {
+                const int x = w0 * 32 + lane;
+                if ((bits >> lane) & 1u) {
+                    int oth; bool ef;
+                    pick(x, oth, ef);
+                    cx.union0((uint32_t)x, (uint32_t)oth);
                 }
                 __syncwarp();  // reconverge: without it the lanes drift apart and replay the loop body per group
             }
