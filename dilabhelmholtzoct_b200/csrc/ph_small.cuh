@@ -645,57 +645,41 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     }
                 }
             }
-            // H1: drop an edge when an ADJACENT edge (parallel neighbour or one sharing a corner) joins the
-            // same two basins and is scanned earlier.  Only the earliest edge between two basins can ever
-            // record a death, and a dropped edge always has an earlier same-pair neighbour, so the earliest
-            // one survives: exact, and it halves the list the merge pass has to walk.
+            // H1: drop an edge when the PARALLEL neighbouring edge (row above / below for a v-edge, column
+            // left / right for an h-edge) joins the same two basins, same sides, and is scanned earlier.
+            // Only the earliest edge between two basins can ever record a death, and a dropped edge always
+            // has an earlier same-pair neighbour, so the earliest one survives: exact.  (Checking the
+            // corner-sharing edges too would halve the list, but costs as many instructions as it saves.)
             if (DIM == 1) {
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     if (!(flags & (3u << (4 * u)))) continue;
                     const int x = x0 + u * nt + lane, r = rr[u], c = cc[u];
-                    const uint32_t L = lab[u];
-                    // labels of the 3x3 neighbourhood (minus the bottom-right cell) from shared memory;
-                    // beyond the image: OUTSIDE (label 0).  Map values are loaded only for the (few)
-                    // neighbours that really join the same two basins.
+                    const uint32_t L = lab[u], l_l = lo1[u], l_u = lo2[u];
                     const bool up = r > 0, dn = r < H - 1, lf = c > 0, rt = c < W - 1;
-                    const uint32_t l_ul = up && lf ? par[x - W - 1] : 0u, l_u = lo2[u], l_ur = up && rt ? par[x - W + 1] : 0u;
-                    const uint32_t l_l = lo1[u], l_r = rt ? par[x + 1] : 0u;
-                    const uint32_t l_dl = dn && lf ? par[x + W - 1] : 0u, l_d = dn ? par[x + W] : 0u;
-                    const float kInfF = __int_as_float(0x7F800000);
-                    const float f_c = g.px(r, c);
-                    // value of the cell (r+dr, c+dc); +inf beyond the image (a boundary edge takes the inside value)
-                    auto cell = [&](int dr, int dc) -> float {
-                        const int rr2 = r + dr, cc2 = c + dc;
-                        return (rr2 < 0 || rr2 >= H || cc2 < 0 || cc2 >= W) ? kInfF : g.px(rr2, cc2);
-                    };
-                    // earlier in the descending scan = larger (value, dense edge id)
-                    auto earlier = [](float vn, int en, float v, int e) { return vn > v || (vn == v && en > e); };
-                    auto same = [](uint32_t p, uint32_t q, uint32_t a, uint32_t b) { return (p == a && q == b) || (p == b && q == a); };
-                    const int e_v = r * GW + W + c, e_h = r * GW + c;  // own left v-edge / top h-edge
-                    if (flags & (1u << (4 * u))) {  // left v-edge: joins l_l | L
-                        const float v = fminf(cell(0, -1), f_c);
+                    const uint32_t l_ul = up && lf ? par[x - W - 1] : 0u;
+                    // earlier in the descending scan = larger (value, dense edge id); the neighbour below /
+                    // right has the larger id, the one above / left the smaller
+                    if (flags & (1u << (4 * u))) {  // left v-edge joins l_l | L
                         bool drop = false;
-                        // parallel v-edges of the row above / below
-                        if (up && same(l_ul, l_u, l_l, L)) drop |= earlier(fminf(cell(-1, -1), cell(-1, 0)), e_v - GW, v, e_v);
-                        if (dn && same(l_dl, l_d, l_l, L)) drop |= earlier(fminf(cell(1, -1), cell(1, 0)), e_v + GW, v, e_v);
-                        // h-edges sharing a corner: top of (r,c), top of (r,c-1), top of (r+1,c), top of (r+1,c-1)
-                        if (same(l_u, L, l_l, L)) drop |= earlier(fminf(cell(-1, 0), f_c), e_h, v, e_v);
-                        if (lf && same(l_ul, l_l, l_l, L)) drop |= earlier(fminf(cell(-1, -1), cell(0, -1)), e_h - 1, v, e_v);
-                        if (dn && same(L, l_d, l_l, L)) drop |= earlier(fminf(f_c, cell(1, 0)), e_h + GW, v, e_v);
-                        if (dn && lf && same(l_l, l_dl, l_l, L)) drop |= earlier(fminf(cell(0, -1), cell(1, -1)), e_h + GW - 1, v, e_v);
+                        const bool m_up = up && l_ul == l_l && l_u == L;
+                        const bool m_dn = dn && (lf ? par[x + W - 1] : 0u) == l_l && par[x + W] == L;
+                        if (m_up || m_dn) {
+                            const float v = lf ? fminf(g.px(r, c - 1), g.px(r, c)) : g.px(r, c);
+                            if (m_up) { const float vn = lf ? fminf(g.px(r - 1, c - 1), g.px(r - 1, c)) : g.px(r - 1, c); drop |= vn > v; }
+                            if (m_dn) { const float vn = lf ? fminf(g.px(r + 1, c - 1), g.px(r + 1, c)) : g.px(r + 1, c); drop |= vn >= v; }
+                        }
                         if (drop) flags &= ~(1u << (4 * u));
                     }
-                    if (flags & (2u << (4 * u))) {  // top h-edge: joins l_u | L
-                        const float v = fminf(cell(-1, 0), f_c);
+                    if (flags & (2u << (4 * u))) {  // top h-edge joins l_u | L
                         bool drop = false;
-                        if (lf && same(l_ul, l_l, l_u, L)) drop |= earlier(fminf(cell(-1, -1), cell(0, -1)), e_h - 1, v, e_h);
-                        if (rt && same(l_ur, l_r, l_u, L)) drop |= earlier(fminf(cell(-1, 1), cell(0, 1)), e_h + 1, v, e_h);
-                        // v-edges sharing a corner: left of (r,c), left of (r,c+1), left of (r-1,c), left of (r-1,c+1)
-                        if (same(l_l, L, l_u, L)) drop |= earlier(fminf(cell(0, -1), f_c), e_v, v, e_h);
-                        if (rt && same(L, l_r, l_u, L)) drop |= earlier(fminf(f_c, cell(0, 1)), e_v + 1, v, e_h);
-                        if (up && same(l_ul, l_u, l_u, L)) drop |= earlier(fminf(cell(-1, -1), cell(-1, 0)), e_v - GW, v, e_h);
-                        if (up && rt && same(l_u, l_ur, l_u, L)) drop |= earlier(fminf(cell(-1, 0), cell(-1, 1)), e_v - GW + 1, v, e_h);
+                        const bool m_lf = lf && l_ul == l_u && l_l == L;
+                        const bool m_rt = rt && (up ? par[x - W + 1] : 0u) == l_u && par[x + 1] == L;
+                        if (m_lf || m_rt) {
+                            const float v = up ? fminf(g.px(r - 1, c), g.px(r, c)) : g.px(r, c);
+                            if (m_lf) { const float vn = up ? fminf(g.px(r - 1, c - 1), g.px(r, c - 1)) : g.px(r, c - 1); drop |= vn > v; }
+                            if (m_rt) { const float vn = up ? fminf(g.px(r - 1, c + 1), g.px(r, c + 1)) : g.px(r, c + 1); drop |= vn >= v; }
+                        }
                         if (drop) flags &= ~(2u << (4 * u));
                     }
                 }
