@@ -142,7 +142,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-constexpr int kStageW = 36;  // floats per staged segment (34 used)
 constexpr int kRing = 64;  // edges per warp in the shared staging ring (two cp.async batches of 32)
 
 // Lock-free Merge of the warp's slice elist[beg..end) as a warp-synchronous state machine.
@@ -610,25 +609,9 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         CrossEdge* elist = S.elist + (size_t)blockIdx.x * S.e_stride;
         // every node owns its left/top edge (H1: pixel) or down/right edge (H0: vertex); the last
         // column / row also own the boundary edges to OUTSIDE (H1).  2 nodes per lane per trip.
-        // H1: the warp stages the map values around its 2 x 32 pixels in shared memory (three flat
-        // segments of 34 floats per group: rows above / own / below, one extra column each side), so
-        // the dedup test and the edge values below need no further global loads
-        float* stage = reinterpret_cast<float*>(smem + kParBytes + kMaskBytes) + warp * (2 * 3 * kStageW);
         for (int x0 = warp * 32; x0 < n_real; x0 += 2 * nt) {  // warp-uniform trip count
             uint32_t lab[2], lo1[2], lo2[2];
             int rr[2], cc[2];
-            if (DIM == 1) {
-                __syncwarp();  // previous trip's readers are done
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        for (int i = lane; i < 34; i += 32) {
-                            const int src = x0 + u * nt + (k - 1) * W - 1 + i;
-                            stage[(u * 3 + k) * kStageW + i] = (src >= 0 && src < N) ? __ldg(g.f + src) : 0.f;
-                        }
-                __syncwarp();
-            }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int x = x0 + u * nt + lane;
@@ -662,48 +645,6 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     }
                 }
             }
-            // H1: drop an edge when the PARALLEL neighbouring edge (row above / below for a v-edge, column
-            // left / right for an h-edge) joins the same two basins, same sides, and is scanned earlier.
-            // Only the earliest edge between two basins can ever record a death, and a dropped edge always
-            // has an earlier same-pair neighbour, so the earliest one survives: exact.  (Checking the
-            // corner-sharing edges too would halve the list, but costs as many instructions as it saves.)
-            if (DIM == 1) {
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (!(flags & (3u << (4 * u)))) continue;
-                    const int x = x0 + u * nt + lane, r = rr[u], c = cc[u];
-                    const uint32_t L = lab[u], l_l = lo1[u], l_u = lo2[u];
-                    const bool up = r > 0, dn = r < H - 1, lf = c > 0, rt = c < W - 1;
-                    const uint32_t l_ul = up && lf ? par[x - W - 1] : 0u;
-                    // earlier in the descending scan = larger (value, dense edge id); the neighbour below /
-                    // right has the larger id, the one above / left the smaller
-                    // staged value of the cell (r+dr, c+dc) (only read where that cell is inside the image)
-                    const float* sg = stage + u * 3 * kStageW + lane + 1;
-#define TL_CELL(dr, dc) sg[((dr) + 1) * kStageW + (dc)]
-                    if (flags & (1u << (4 * u))) {  // left v-edge joins l_l | L
-                        bool drop = false;
-                        const bool m_up = up && l_ul == l_l && l_u == L;
-                        const bool m_dn = dn && (lf ? par[x + W - 1] : 0u) == l_l && par[x + W] == L;
-                        if (m_up || m_dn) {
-                            const float v = lf ? fminf(TL_CELL(0, -1), TL_CELL(0, 0)) : TL_CELL(0, 0);
-                            if (m_up) { const float vn = lf ? fminf(TL_CELL(-1, -1), TL_CELL(-1, 0)) : TL_CELL(-1, 0); drop |= vn > v; }
-                            if (m_dn) { const float vn = lf ? fminf(TL_CELL(1, -1), TL_CELL(1, 0)) : TL_CELL(1, 0); drop |= vn >= v; }
-                        }
-                        if (drop) flags &= ~(1u << (4 * u));
-                    }
-                    if (flags & (2u << (4 * u))) {  // top h-edge joins l_u | L
-                        bool drop = false;
-                        const bool m_lf = lf && l_ul == l_u && l_l == L;
-                        const bool m_rt = rt && (up ? par[x - W + 1] : 0u) == l_u && par[x + 1] == L;
-                        if (m_lf || m_rt) {
-                            const float v = up ? fminf(TL_CELL(-1, 0), TL_CELL(0, 0)) : TL_CELL(0, 0);
-                            if (m_lf) { const float vn = up ? fminf(TL_CELL(-1, -1), TL_CELL(0, -1)) : TL_CELL(0, -1); drop |= vn > v; }
-                            if (m_rt) { const float vn = up ? fminf(TL_CELL(-1, 1), TL_CELL(0, 1)) : TL_CELL(0, 1); drop |= vn >= v; }
-                        }
-                        if (drop) flags &= ~(2u << (4 * u));
-                    }
-                }
-            }
             const int cnt = __popc(flags);
             int incl = cnt;
 #pragma unroll
@@ -722,17 +663,10 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     if (flags & (1u << (4 * u + k))) {
                         uint32_t lo = 0u, pos;
                         float val;
-                        if (DIM == 1) {
-                            const float* sg = stage + u * 3 * kStageW + lane + 1;
-                            const float fc = TL_CELL(0, 0);
-                            if (k == 0) { lo = lo1[u]; pos = (uint32_t)(r * GW + W + c); val = c > 0 ? fminf(TL_CELL(0, -1), fc) : fc; }
-                            else if (k == 1) { lo = lo2[u]; pos = (uint32_t)(r * GW + c); val = r > 0 ? fminf(TL_CELL(-1, 0), fc) : fc; }
-                            else if (k == 2) { pos = (uint32_t)(r * GW + 2 * W); val = fc; }
-                            else { pos = (uint32_t)(H * GW + c); val = fc; }
-                        } else {
-                            if (k == 0) { lo = lo1[u]; pos = (uint32_t)(r * GW + W + c); val = g.vedge_val(r, c); }
-                            else { lo = lo2[u]; pos = (uint32_t)(r * GW + c); val = g.hedge_val(r, c); }
-                        }
+                        if (k == 0) { lo = lo1[u]; pos = (uint32_t)(r * GW + W + c); val = g.vedge_val(r, c); }
+                        else if (k == 1) { lo = lo2[u]; pos = (uint32_t)(r * GW + c); val = g.hedge_val(r, c); }
+                        else if (k == 2) { pos = (uint32_t)(r * GW + 2 * W); val = g.px(r, c); }
+                        else { pos = (uint32_t)(H * GW + c); val = g.px(r, c); }
                         CrossEdge ce;
                         ce.skey = g.make_ekey(val, pos); ce.la = lo; ce.lb = lab[u];
                         elist[slot++] = ce;
@@ -740,7 +674,6 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 }
             }
         }
-#undef TL_CELL
         __syncthreads();  // every basin id has been read: the union-find storage can become the table
         if (packed) {
             for (int c = tid; c <= K; c += nt) { T64[c] = (~0ull << Gbits) | (uint32_t)c; Z32[c] = c ? zvalg[c] : 0u; }
