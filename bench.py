@@ -265,7 +265,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "masks/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(pred_h.numel() * 4 + truth_h.numel() * 4), "d2h_bytes_per_step": 4,
                 "api": f"topo_loss_from_host(pinned pred, pinned truth, chunks={E2E_CHUNKS}): H2D pipelined against the kernels"},
-        "gpu_launches": 5 * args.steps,
+        "gpu_launches": 4 * args.steps,  # persistence, matching, loss, grad scatter (+ 2 memsets) per step
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

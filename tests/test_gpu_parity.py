@@ -319,3 +319,21 @@ def test_loss_1024_small_batch():
     pred, truth = make_batch(1, 1024, 1024, seed=55, n_classes=3)
     pred = torch.cat([pred, pred.flip(-1)]); truth = torch.cat([truth, truth.flip(-1)])
     _check_loss(pred, truth, 0.1, 1)
+
+
+def test_wasserstein_large_truth_diagrams():
+    """Both diagrams large (hundreds of points): the assignment is no longer the easy tall-skinny case."""
+    import dilabhelmholtzoct_b200 as tlb
+    rng = np.random.default_rng(17)
+    D1, D2 = [], []
+    for n, m in ((300, 280), (150, 400), (257, 1), (1, 257), (0, 50), (50, 0)):
+        b = rng.random(n).astype(np.float32)
+        D1.append(np.stack([b, b + rng.random(n).astype(np.float32)], 1).reshape(-1, 2))
+        b = rng.random(m).astype(np.float32)
+        D2.append(np.stack([b, b + rng.random(m).astype(np.float32)], 1).reshape(-1, 2))
+    cost, match = tlb.wasserstein_cost([torch.tensor(d, device="cuda") for d in D1],
+                                       [torch.tensor(d, device="cuda") for d in D2], 2.0)
+    cost = cost.cpu().numpy()
+    for k in range(len(D1)):
+        want, _ = oracle.wasserstein(D1[k], D2[k], 2.0)
+        assert abs(cost[k] - want) <= 1e-9 + 1e-7 * abs(want), (k, cost[k], want)
