@@ -1,5 +1,6 @@
-// Shared-memory persistence kernel for maps with at most 65535 nodes (+ OUTSIDE): 50x50 .. 256x256.
-// One CTA per (image, class) map; same algorithm as ph_kernel.cuh (elder-linked union-find, then a
+// Shared-memory persistence kernel.  One CTA per (image, class) map; maps with more than 65535 nodes
+// are processed in BANDS of whole node rows (16-bit node ids local to the band; a 256x256 H1 map is a
+// single band); same algorithm as ph_kernel.cuh (elder-linked union-find, then a
 // lock-free triplet merge tree), but every latency-critical structure lives in shared memory:
 //
 //   phase A  level-0 union-find on 16-bit parents        par[65536]            (128 KB)
@@ -18,7 +19,7 @@
 
 namespace tl {
 
-constexpr int kSmallMaxNodes = 65535;
+constexpr int kSmallMaxRow = 4097;   // nodes per row (the previous band's last-row labels live in shared memory)
 constexpr uint32_t kOut16 = 0xFFFFu;
 constexpr uint64_t kRootKey = ~0ull;
 constexpr int kParBytes = 65536 * 2;
@@ -301,7 +302,8 @@ template <int DIM>
 struct SmallCtx {
     Geo<DIM> g;
     uint16_t* par;
-    __device__ __forceinline__ SmallCtx(const float* f, int H, int W, uint16_t* par_) : g(f, H, W), par(par_) {}
+    int base;  // global id of the band's first node (ids in par[] are local to the band)
+    __device__ __forceinline__ SmallCtx(const float* f, int H, int W, uint16_t* par_) : g(f, H, W), par(par_), base(0) {}
 
     __device__ __forceinline__ uint32_t find(uint32_t x) const {
         volatile uint16_t* p = par;
@@ -326,7 +328,7 @@ struct SmallCtx {
             if (x == kOut16) return true;
             if (y == kOut16) return false;
         }
-        return g.nkey((int)x) < g.nkey((int)y);
+        return g.nkey(base + (int)x) < g.nkey(base + (int)y);
     }
     __device__ void union0(uint32_t a, uint32_t b) {
         for (;;) {
@@ -379,11 +381,9 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         SmallCtx<DIM> cx(A.maps[set] + (size_t)map * N, H, W, par);
         const Geo<DIM>& g = cx.g;
         const int NN = g.NN, GW = g.GW, VW = g.VW;
-        const int n_real = DIM == 1 ? N : NN;  // nodes that own a slot besides OUTSIDE
 
         // ---- phase 0: init, argmax (H0), and the constant-map shortcut (absent classes give all-zero
         //      ground-truth maps: no finite pair; H0 keeps only the essential class (0 -> argmax = 0))
-        for (int x = tid; x < 65536; x += nt) par[x] = (uint16_t)x;
         {
             unsigned long long best = 0ull;
             uint32_t lo = 0xFFFFFFFFu, hi = 0u;
@@ -436,11 +436,22 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             continue;
         }
 
-        // ---- phase 1: level-0 union-find in shared memory
-        const bool alias = DIM == 1 && N == 65536;  // last pixel == OUTSIDE
-        const FastDiv divW((uint32_t)W), divVW((uint32_t)VW), divW1((uint32_t)(W + 1));
-        // pick(x): far end of x's earliest incident edge when that edge has x's own value (else -1), and
-        // whether that far end is known to be ELDER than x from registers alone
+        // ---- phases 1-3 run per BAND of whole node rows (<= 65535 nodes, 16-bit ids local to the band;
+        //      a 256x256 H1 map is one band).  Level-0 links never leave a band: a node whose earliest
+        //      edge crosses the band border stays the root of its sub-basin and that edge is handed to
+        //      the merge tree as an ordinary crossing edge.  This is still exact: forest paths stay
+        //      key-monotone, a sub-basin root is the eldest node of its sub-basin, and the deferred merge
+        //      has zero persistence.
+        const int rowlen = DIM == 1 ? W : VW, n_rows = DIM == 1 ? H : H + 1;
+        const bool alias = DIM == 1 && N == 65536;  // single band whose last pixel doubles as OUTSIDE
+        const int rows_per_band = alias ? n_rows : min(n_rows, 65535 / rowlen);
+        const FastDiv divW((uint32_t)W), divVW((uint32_t)VW);
+        uint32_t* prev_lab = reinterpret_cast<uint32_t*>(smem + kParBytes + kMaskBytes);  // labels of the previous band's last row
+        CrossEdge* elist = S.elist + (size_t)blockIdx.x * S.e_stride;
+        int cid_base = 0;  // basins found in earlier bands
+        // pick(x): far end (GLOBAL node id, kOut16 for OUTSIDE) of x's earliest incident edge when that
+        // edge has x's own value (else -1), and whether that far end is known to be ELDER than x from
+        // registers alone
         auto pick = [&](int x, int& oth, bool& elder_far) {
             oth = -1; elder_far = false;
             if (DIM == 1) {
@@ -452,18 +463,19 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 // value is fp whenever the far pixel is >= fp (or the edge is a boundary edge), and
                 // among those the bitmap position orders bottom > right > left > top
                 float fo = fp;
-                if (r == H - 1) oth = (int)kOut16;
+                bool out = false;
+                if (r == H - 1) out = true;
                 else if (fd >= fp) { oth = x + W; fo = fd; }
-                else if (c == W - 1) oth = (int)kOut16;
+                else if (c == W - 1) out = true;
                 else if (fr >= fp) { oth = x + 1; fo = fr; }
-                else if (c == 0) oth = (int)kOut16;
+                else if (c == 0) out = true;
                 else if (fl >= fp) { oth = x - 1; fo = fl; }
-                else if (r == 0) oth = (int)kOut16;
+                else if (r == 0) out = true;
                 else if (fu >= fp) { oth = x - W; fo = fu; }
                 // else: strict local maximum, stays a root
                 // strictly higher, OUTSIDE, or equal with a larger raster index: elder than x
-                elder_far = oth == (int)kOut16 || fo > fp || (fo == fp && oth > x);
-                if (alias && oth == N - 1) { oth = (int)kOut16; elder_far = true; }
+                elder_far = out || fo > fp || (fo == fp && oth > x);
+                if (out || (alias && oth == N - 1)) { oth = (int)kOut16; elder_far = true; }
             } else {
                 uint64_t best = ~0ull;
                 const int i = (int)divVW.div((uint32_t)x), j = x - i * VW;
@@ -485,110 +497,210 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 }
             }
         };
-        // phase 1a: a node whose far end is elder by registers just POINTS at it -- a plain store to
-        // its own entry, no atomics, no find (every entry has one writer in this phase).  The others
-        // (ties towards a smaller raster index; every H0 vertex) are flagged for phase 1b.
-        // 4 nodes per lane per trip so that the 4 x 5 map loads are in flight together.
-        for (int x0 = warp * 32; x0 < n_real; x0 += 4 * nt) {  // warp-uniform trip count
-            int other[4];
-            bool elder_far[4];
+        for (int r0 = 0; r0 < n_rows; r0 += rows_per_band) {
+            const int r1 = min(n_rows, r0 + rows_per_band);
+            const int base = r0 * rowlen, nb = (r1 - r0) * rowlen;  // this band: global nodes base .. base+nb-1
+            cx.base = base;
+            // far end as a band-local id: kOut16 stays, nodes outside the band give -1 (no level-0 link)
+            auto local_of = [&](int oth) { return oth < 0 ? -1 : oth == (int)kOut16 ? (int)kOut16 : (oth >= base && oth < base + nb) ? oth - base : -1; };
+            __syncthreads();
+            for (int x = tid; x < 65536; x += nt) par[x] = (uint16_t)x;
+            __syncthreads();
+            // phase 1a: a node whose far end is elder by registers just POINTS at it -- a plain store to
+            // its own entry, no atomics, no find (every entry has one writer in this phase).  The others
+            // (ties towards a smaller raster index; every H0 vertex) are flagged for phase 1b.
+            // 4 nodes per lane per trip so that the 4 x 5 map loads are in flight together.
+            for (int x0 = warp * 32; x0 < nb; x0 += 4 * nt) {  // warp-uniform trip count
+                int other[4];
+                bool elder_far[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int x = x0 + u * nt + lane;
-                other[u] = -1; elder_far[u] = false;
-                if (x < n_real && !(alias && x == N - 1)) pick(x, other[u], elder_far[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int x = x0 + u * nt + lane;
-                const bool direct = other[u] >= 0 && elder_far[u];
-                if (direct) par[x] = (uint16_t)other[u];
-                const unsigned deferred = __ballot_sync(0xFFFFFFFFu, other[u] >= 0 && !direct);
-                if (lane == 0 && x0 + u * nt < n_real) mask[(x0 + u * nt) >> 5] = deferred;
-            }
-        }
-        __syncthreads();
-        // phase 1b: elder-linked lock-free unions (CAS on the younger root) for the flagged nodes
-        for (int w0 = warp; w0 < ((n_real + 31) >> 5); w0 += nt >> 5) {
-            const unsigned bits = mask[w0];
-            if (bits) {
-                const int x = w0 * 32 + lane;
-                if ((bits >> lane) & 1u) {
-                    int oth; bool ef;
-                    pick(x, oth, ef);
-                    cx.union0((uint32_t)x, (uint32_t)oth);
+                for (int u = 0; u < 4; ++u) {
+                    const int xl = x0 + u * nt + lane;
+                    other[u] = -1; elder_far[u] = false;
+                    if (xl < nb && !(alias && xl == N - 1)) { pick(base + xl, other[u], elder_far[u]); other[u] = local_of(other[u]); }
                 }
-                __syncwarp();  // reconverge: without it the lanes drift apart and replay the loop body per group
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int xl = x0 + u * nt + lane;
+                    const bool direct = other[u] >= 0 && elder_far[u];
+                    if (direct) par[xl] = (uint16_t)other[u];
+                    const unsigned deferred = __ballot_sync(0xFFFFFFFFu, other[u] >= 0 && !direct);
+                    if (lane == 0 && x0 + u * nt < nb) mask[(x0 + u * nt) >> 5] = deferred;
+                }
             }
-        }
-        __syncthreads();
-        TL_PROF(1);
-        // flatten by pointer jumping: each round every node adopts its grandparent (own entry only,
-        // so no store can regress another thread's result); depth halves per round
-        for (;;) {
-            int changed = 0;
+            __syncthreads();
+            // phase 1b: elder-linked lock-free unions (CAS on the younger root) for the flagged nodes
+            for (int w0 = warp; w0 < ((nb + 31) >> 5); w0 += nt >> 5) {
+                const unsigned bits = mask[w0];
+                if (bits) {
+                    const int xl = w0 * 32 + lane;
+                    if ((bits >> lane) & 1u) {
+                        int oth; bool ef;
+                        pick(base + xl, oth, ef);
+                        oth = local_of(oth);
+                        if (oth >= 0) cx.union0((uint32_t)xl, (uint32_t)oth);
+                    }
+                    __syncwarp();  // reconverge: without it the lanes drift apart and replay the loop body per group
+                }
+            }
+            __syncthreads();
+            TL_PROF(1);
+            // flatten by pointer jumping: each round every node adopts its grandparent (own entry only,
+            // so no store can regress another thread's result); depth halves per round
+            for (;;) {
+                int changed = 0;
 #pragma unroll 4
-            for (int x = tid; x < n_real; x += nt) {
-                const uint32_t p = par[x];
-                const uint32_t gp = par[p];
-                if (gp != p) { par[x] = (uint16_t)gp; changed = 1; }
+                for (int x = tid; x < nb; x += nt) {
+                    const uint32_t p = par[x];
+                    const uint32_t gp = par[p];
+                    if (gp != p) { par[x] = (uint16_t)gp; changed = 1; }
+                }
+                if (!__syncthreads_or(changed)) break;
             }
-            if (!__syncthreads_or(changed)) break;
-        }
-        TL_PROF(2);
+            TL_PROF(2);
 
-        // ---- census: dense basin ids in raster order of the roots
-        const int chunk = (((n_real + 31) / 32) + 31) & ~31;
-        const int beg = min(n_real, warp * chunk), end = min(n_real, beg + chunk);
-        {
-            int cnt = 0;
-            for (int i0 = beg; i0 < end; i0 += 32) {
-                const int i = i0 + lane;
-                const bool root = i < end && par[i] == (uint16_t)i && !(DIM == 1 && (uint32_t)i == kOut16);
-                cnt += __popc(__ballot_sync(0xFFFFFFFFu, root));
-            }
-            if (lane == 0) s_wcnt[warp] = cnt;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            const int v = s_wcnt[lane];
-            int incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
-            s_wcnt[lane] = incl - v;
-            if (lane == 31) s_K = incl;
-        }
-        __syncthreads();
-        const int K = s_K;  // basins 1..K (0 = OUTSIDE for H1, unused for H0)
-        {
-            int run = s_wcnt[warp];
-            for (int i0 = beg; i0 < end; i0 += 32) {
-                const int i = i0 + lane;
-                const bool root = i < end && par[i] == (uint16_t)i && !(DIM == 1 && (uint32_t)i == kOut16);
-                const unsigned bal = __ballot_sync(0xFFFFFFFFu, root);
-                if (lane == 0) mask[i0 >> 5] = bal;
-                if (root) {
-                    const int cid = 1 + run + __popc(bal & lanemask_lt());
-                    rootpix[cid] = (uint32_t)i;
-                    zvalg[cid] = (uint32_t)(g.nkey(i) >> 32);
-                    par[i] = (uint16_t)cid;
+            // ---- census: dense basin ids in raster order of the roots (bands are row ranges, so ids
+            //      stay in global raster order across bands)
+            const int chunk = (((nb + 31) / 32) + 31) & ~31;
+            const int beg = min(nb, warp * chunk), end = min(nb, beg + chunk);
+            {
+                int cnt = 0;
+                for (int i0 = beg; i0 < end; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool root = i < end && par[i] == (uint16_t)i && !(DIM == 1 && (uint32_t)i == kOut16);
+                    cnt += __popc(__ballot_sync(0xFFFFFFFFu, root));
                 }
-                run += __popc(bal);
+                if (lane == 0) s_wcnt[warp] = cnt;
             }
-        }
-        __syncthreads();
+            __syncthreads();
+            if (warp == 0) {
+                const int v = s_wcnt[lane];
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+                s_wcnt[lane] = incl - v;
+                if (lane == 31) s_K = incl;
+            }
+            __syncthreads();
+            const int Kb = s_K;  // basins of this band: global ids cid_base+1 .. cid_base+Kb
+            {
+                int run = s_wcnt[warp];
+                for (int i0 = beg; i0 < end; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool root = i < end && par[i] == (uint16_t)i && !(DIM == 1 && (uint32_t)i == kOut16);
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, root);
+                    if (lane == 0) mask[i0 >> 5] = bal;
+                    if (root) {
+                        const int rank = run + __popc(bal & lanemask_lt());  // 0-based inside the band
+                        if (cid_base + 1 + rank < (int)S.k_stride) {
+                            rootpix[cid_base + 1 + rank] = (uint32_t)(base + i);
+                            zvalg[cid_base + 1 + rank] = (uint32_t)(g.nkey(base + i) >> 32);
+                        }
+                        par[i] = (uint16_t)rank;
+                    }
+                    run += __popc(bal);
+                }
+            }
+            __syncthreads();
+            // per-node label in place: band-local basin rank, kOut16 for OUTSIDE's basin
 #pragma unroll 4
-        for (int x = tid; x < n_real; x += nt) {
-            uint32_t b;
-            if ((mask[x >> 5] >> (x & 31)) & 1u) b = par[x];
-            else {
-                const uint32_t r = par[x];
-                b = (DIM == 1 && r == kOut16) ? 0u : par[r];
+            for (int x = tid; x < nb; x += nt) {
+                uint32_t b;
+                if ((mask[x >> 5] >> (x & 31)) & 1u) b = par[x];
+                else {
+                    const uint32_t r = par[x];
+                    b = (DIM == 1 && r == kOut16) ? kOut16 : par[r];
+                }
+                par[x] = (uint16_t)b;  // after the flatten nobody reads a non-root entry, roots keep their rank
             }
-            par[x] = (uint16_t)b;  // in place: after the flatten nobody reads a non-root entry, roots keep their id
+            __syncthreads();
+            TL_PROF(3);
+
+            // ---- compaction: the edges that cross two basins go to a per-CTA list.  Every node owns the
+            //      edge to its left and the edge above it (H1: pixel; H0: vertex), so only the "above" edge
+            //      can cross into the previous band, whose last-row labels are kept in prev_lab; H1's last
+            //      column / row also own the boundary edges to OUTSIDE.  `pos` below is the DENSE edge id:
+            //      rank of the edge among edges in bitmap order (bitmap row pair i holds W h-edges then W+1
+            //      v-edges), order-isomorphic to the bitmap position.  2 nodes per lane per trip.
+            auto glabel = [&](uint32_t v) { return v == kOut16 ? 0u : (uint32_t)(cid_base + 1) + v; };
+            for (int x0 = warp * 32; x0 < nb; x0 += 2 * nt) {  // warp-uniform trip count
+                uint32_t lab[2], lo1[2], lo2[2];
+                int rr[2], cc[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int xl = x0 + u * nt + lane;
+                    lab[u] = lo1[u] = lo2[u] = 0u; rr[u] = cc[u] = 0;
+                    if (xl < nb) {
+                        const int x = base + xl;
+                        rr[u] = (int)(DIM == 1 ? divW.div((uint32_t)x) : divVW.div((uint32_t)x)); cc[u] = x - rr[u] * rowlen;
+                        lab[u] = glabel(par[xl]);
+                        const bool first_row = rr[u] == r0;
+                        if (DIM == 1) {
+                            lo1[u] = cc[u] == 0 ? 0u : glabel(par[xl - 1]);                        // left v-edge
+                            lo2[u] = rr[u] == 0 ? 0u : first_row ? prev_lab[cc[u]] : glabel(par[xl - W]);  // top h-edge
+                        } else {
+                            lo1[u] = rr[u] == 0 ? lab[u] : first_row ? prev_lab[cc[u]] : glabel(par[xl - VW]);  // up v-edge
+                            lo2[u] = cc[u] == 0 ? lab[u] : glabel(par[xl - 1]);                    // left h-edge
+                        }
+                    }
+                }
+                // count this lane's crossing edges (at most 8 flags), ONE warp scan + ONE atomic per trip,
+                // then form and store the records
+                unsigned flags = 0u;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int xl = x0 + u * nt + lane;
+                    if (xl < nb) {
+                        if (lo1[u] != lab[u]) flags |= 1u << (4 * u);
+                        if (lo2[u] != lab[u]) flags |= 2u << (4 * u);
+                        if (DIM == 1) {
+                            if (cc[u] == W - 1 && lab[u] != 0u) flags |= 4u << (4 * u);
+                            if (rr[u] == H - 1 && lab[u] != 0u) flags |= 8u << (4 * u);
+                        }
+                    }
+                }
+                const int cnt = __popc(flags);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+                int slot = 0;
+                if (lane == 31 && incl > 0) slot = atomicAdd(&s_ncross, incl);
+                slot = __shfl_sync(0xFFFFFFFFu, slot, 31) + incl - cnt;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int r = rr[u], c = cc[u];
+#pragma unroll
+                    for (int k = 0; k < (DIM == 1 ? 4 : 2); ++k) {
+                        // k = 0 / 1: the two owned edges; k = 2 / 3: right / bottom boundary edges (H1 only)
+                        if (flags & (1u << (4 * u + k))) {
+                            uint32_t lo = 0u, pos;
+                            float val;
+                            if (DIM == 1) {
+                                if (k == 0) { lo = lo1[u]; pos = (uint32_t)(r * GW + W + c); val = g.vedge_val(r, c); }
+                                else if (k == 1) { lo = lo2[u]; pos = (uint32_t)(r * GW + c); val = g.hedge_val(r, c); }
+                                else if (k == 2) { pos = (uint32_t)(r * GW + 2 * W); val = g.px(r, c); }
+                                else { pos = (uint32_t)(H * GW + c); val = g.px(r, c); }
+                            } else {
+                                // vertex (r,c): up v-edge(r-1,c) joins (r-1,c),(r,c); left h-edge(r,c-1) joins (r,c-1),(r,c)
+                                if (k == 0) { lo = lo1[u]; pos = (uint32_t)((r - 1) * GW + W + c); val = g.vedge_val(r - 1, c); }
+                                else { lo = lo2[u]; pos = (uint32_t)(r * GW + c - 1); val = g.hedge_val(r, c - 1); }
+                            }
+                            CrossEdge ce;
+                            ce.skey = g.make_ekey(val, pos); ce.la = lo; ce.lb = lab[u];
+                            if (slot < (int)S.e_stride) elist[slot] = ce;
+                            ++slot;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // labels of this band's last row, for the next band's "above" edges
+            if (r1 < n_rows)
+                for (int j = tid; j < rowlen; j += nt) prev_lab[j] = glabel(par[nb - rowlen + j]);
+            cid_base += Kb;
+            TL_PROF(6);
         }
-        __syncthreads();
-        TL_PROF(3);
+        const int K = cid_base;  // basins 1..K (0 = OUTSIDE for H1, unused for H0)
 
         // ---- phase B: triplet merge tree over basins
         // packed 64-bit entries when edge id + basin id fit 32 bits next to the 32-bit value (always
@@ -605,75 +717,6 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         PK.t_s = T.s; PK.z_s = T.s + (uint32_t)(((K + 1) * 8 + 15) & ~15); PK.G = Gbits; PK.gmask = (1u << Gbits) - 1u;
         uint64_t* T64 = reinterpret_cast<uint64_t*>(smem);
         uint32_t* Z32 = reinterpret_cast<uint32_t*>(smem + (((K + 1) * 8 + 15) & ~15));
-        // pass 1 (streaming): compact the edges that cross two basins into a per-CTA list
-        CrossEdge* elist = S.elist + (size_t)blockIdx.x * S.e_stride;
-        // every node owns its left/top edge (H1: pixel) or down/right edge (H0: vertex); the last
-        // column / row also own the boundary edges to OUTSIDE (H1).  2 nodes per lane per trip.
-        for (int x0 = warp * 32; x0 < n_real; x0 += 2 * nt) {  // warp-uniform trip count
-            uint32_t lab[2], lo1[2], lo2[2];
-            int rr[2], cc[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int x = x0 + u * nt + lane;
-                lab[u] = lo1[u] = lo2[u] = 0u; rr[u] = cc[u] = 0;
-                if (x < n_real) {
-                    if (DIM == 1) {
-                        rr[u] = (int)divW.div((uint32_t)x); cc[u] = x - rr[u] * W;
-                        lab[u] = par[x];
-                        lo1[u] = cc[u] == 0 ? 0u : par[x - 1];   // across the left v-edge
-                        lo2[u] = rr[u] == 0 ? 0u : par[x - W];   // across the top h-edge
-                    } else {
-                        rr[u] = (int)divVW.div((uint32_t)x); cc[u] = x - rr[u] * VW;
-                        lab[u] = par[x];
-                        lo1[u] = rr[u] < H ? par[x + VW] : lab[u];  // down v-edge
-                        lo2[u] = cc[u] < W ? par[x + 1] : lab[u];   // right h-edge
-                    }
-                }
-            }
-            // count this lane's crossing edges (at most 8 flags), ONE warp scan + ONE atomic per trip,
-            // then form and store the records
-            unsigned flags = 0u;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int x = x0 + u * nt + lane;
-                if (x < n_real) {
-                    if (lo1[u] != lab[u]) flags |= 1u << (4 * u);
-                    if (lo2[u] != lab[u]) flags |= 2u << (4 * u);
-                    if (DIM == 1) {
-                        if (cc[u] == W - 1 && lab[u] != 0u) flags |= 4u << (4 * u);
-                        if (rr[u] == H - 1 && lab[u] != 0u) flags |= 8u << (4 * u);
-                    }
-                }
-            }
-            const int cnt = __popc(flags);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
-            int slot = 0;
-            if (lane == 31 && incl > 0) slot = atomicAdd(&s_ncross, incl);
-            slot = __shfl_sync(0xFFFFFFFFu, slot, 31) + incl - cnt;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int r = rr[u], c = cc[u];
-#pragma unroll
-                for (int k = 0; k < (DIM == 1 ? 4 : 2); ++k) {
-                    // k = 0: v-edge, k = 1: h-edge, k = 2 / 3: right / bottom boundary edges (H1 only).
-                    // `pos` is the DENSE edge id: rank of the edge among edges in bitmap order (row i of the
-                    // bitmap pair holds W h-edges then W+1 v-edges), order-isomorphic to the bitmap position
-                    if (flags & (1u << (4 * u + k))) {
-                        uint32_t lo = 0u, pos;
-                        float val;
-                        if (k == 0) { lo = lo1[u]; pos = (uint32_t)(r * GW + W + c); val = g.vedge_val(r, c); }
-                        else if (k == 1) { lo = lo2[u]; pos = (uint32_t)(r * GW + c); val = g.hedge_val(r, c); }
-                        else if (k == 2) { pos = (uint32_t)(r * GW + 2 * W); val = g.px(r, c); }
-                        else { pos = (uint32_t)(H * GW + c); val = g.px(r, c); }
-                        CrossEdge ce;
-                        ce.skey = g.make_ekey(val, pos); ce.la = lo; ce.lb = lab[u];
-                        elist[slot++] = ce;
-                    }
-                }
-            }
-        }
         __syncthreads();  // every basin id has been read: the union-find storage can become the table
         if (packed) {
             for (int c = tid; c <= K; c += nt) { T64[c] = (~0ull << Gbits) | (uint32_t)c; Z32[c] = c ? zvalg[c] : 0u; }

@@ -96,7 +96,8 @@ Layout make_layout(int M, int H, int W, int dim, int B) {
     for (int s = 0; s < 2; ++s) L.pairs[s] = take(sizeof(tl::PairRec) * (size_t)M * L.cap);
     for (int s = 0; s < 2; ++s) L.skeys[s] = take(sizeof(uint64_t) * (size_t)M * L.cap);
     L.match1 = take(sizeof(int32_t) * (size_t)M * L.cap);
-    L.small = dim == 1 ? ((long long)H * W <= 65536) : (L.n_nodes <= tl::kSmallMaxNodes);
+    // shared-memory kernel: processes the map in bands of whole node rows (<= 65535 nodes each)
+    L.small = (W + 1) <= tl::kSmallMaxRow && (long long)L.n_nodes < (1ll << 22);
     if (L.small) {
         L.k_stride = align_up((size_t)L.cap + 2, 64);
         L.rootpix = take(sizeof(uint32_t) * L.k_stride * kSmallSlots);
@@ -104,9 +105,13 @@ Layout make_layout(int M, int H, int W, int dim, int B) {
         L.T2g = take(sizeof(tl::TEntry) * L.k_stride * kSmallSlots);
         L.e_stride = align_up((size_t)H * (W + 1) + (size_t)(H + 1) * W, 64);
         L.elist = take(sizeof(tl::CrossEdge) * L.e_stride * kSmallSlots);
-    } else {
-        L.t_stride = align_up(sizeof(uint64_t) * (size_t)L.n_nodes) / sizeof(uint64_t);
-        L.T = take(sizeof(uint64_t) * L.t_stride * kPhSlots);
+    }
+    {
+        const char* fg = getenv("TL_FORCE_GLOBAL");
+        if (!L.small || (fg && fg[0] == '1')) {
+            L.t_stride = align_up(sizeof(uint64_t) * (size_t)L.n_nodes) / sizeof(uint64_t);
+            L.T = take(sizeof(uint64_t) * L.t_stride * kPhSlots);
+        }
     }
     L.key_tmp = take(sizeof(uint64_t) * (size_t)L.cap * kSortSlots);
     L.idx_a = take(sizeof(uint32_t) * (size_t)L.cap * kSortSlots);
@@ -151,7 +156,11 @@ int launch_ph(const float* m0, const float* m1, int n_sets, const Layout& L, int
     TL_CUDA(cudaMemsetAsync(a.job_counter, 0, 256, st));
     long long jobs = (long long)n_sets * L.M;
     int grid = (int)(jobs < kPhSlots ? jobs : kPhSlots);
-    if (L.small) {
+    // TL_FORCE_GLOBAL=1 (tests) routes every shape through the global-memory kernel, which otherwise only
+    // serves maps wider than kSmallMaxRow
+    const char* fg = getenv("TL_FORCE_GLOBAL");
+    const bool use_small = L.small && !(fg && fg[0] == '1');
+    if (use_small) {
         static int n_sm = 0;
         if (n_sm == 0) {
             int dev = 0, v = 0;

@@ -74,11 +74,22 @@ def test_pairs_signed_and_negative_zero(dim):
 
 
 @pytest.mark.parametrize("dim", [0, 1])
-def test_pairs_large_map_global_kernel(dim):
-    """> 65535 nodes: the global-memory kernel (ph_kernel) instead of the shared-memory one."""
+def test_pairs_banded_maps(dim):
+    """> 65535 nodes: the shared-memory kernel works through the map in bands of whole rows."""
     rng = np.random.default_rng(5)
     maps = rng.random((3, 300, 300)).astype(np.float32)
     maps[2] = np.round(maps[2] * 8) / 8
+    _assert_same_pairs(maps, dim)
+
+
+@pytest.mark.parametrize("dim", [0, 1])
+def test_pairs_global_memory_kernel(dim, monkeypatch):
+    """The global-memory kernel (maps wider than the shared-memory kernel's row limit), forced here."""
+    monkeypatch.setenv("TL_FORCE_GLOBAL", "1")
+    rng = np.random.default_rng(8)
+    maps = rng.random((3, 70, 70)).astype(np.float32)
+    maps[1] = np.round(maps[1] * 4) / 4
+    maps[2] = (maps[2] > 0.5).astype(np.float32)
     _assert_same_pairs(maps, dim)
 
 
