@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         uint32_t* prev_lab = reinterpret_cast<uint32_t*>(smem + kParBytes + kMaskBytes);  // labels of the previous band's last row
         CrossEdge* elist = S.elist + (size_t)blockIdx.x * S.e_stride;
         int cid_base = 0;  // basins found in earlier bands
-        // pick(x): far end (GLOBAL node id, kOut16 for OUTSIDE) of x's earliest incident edge when that
+        // pick(x): far end (GLOBAL node id, -2 for OUTSIDE) of x's earliest incident edge when that
         // edge has x's own value (else -1), and whether that far end is known to be ELDER than x from
         // registers alone
         auto pick = [&](int x, int& oth, bool& elder_far) {
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 // else: strict local maximum, stays a root
                 // strictly higher, OUTSIDE, or equal with a larger raster index: elder than x
                 elder_far = out || fo > fp || (fo == fp && oth > x);
-                if (out || (alias && oth == N - 1)) { oth = (int)kOut16; elder_far = true; }
+                if (out || (alias && oth == N - 1)) { oth = -2; elder_far = true; }
             } else {
                 uint64_t best = ~0ull;
                 const int i = (int)divVW.div((uint32_t)x), j = x - i * VW;
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             const int base = r0 * rowlen, nb = (r1 - r0) * rowlen;  // this band: global nodes base .. base+nb-1
             cx.base = base;
             // far end as a band-local id: kOut16 stays, nodes outside the band give -1 (no level-0 link)
-            auto local_of = [&](int oth) { return oth < 0 ? -1 : oth == (int)kOut16 ? (int)kOut16 : (oth >= base && oth < base + nb) ? oth - base : -1; };
+            auto local_of = [&](int oth) { return oth == -2 ? (int)kOut16 : (oth >= base && oth < base + nb) ? oth - base : -1; };
             __syncthreads();
             for (int x = tid; x < 65536; x += nt) par[x] = (uint16_t)x;
             __syncthreads();
