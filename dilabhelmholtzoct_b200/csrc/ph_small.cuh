@@ -760,8 +760,6 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         PairRec* out = A.pairs[set] + (size_t)map * A.cap;
         uint64_t* skeys = A.skeys[set] ? A.skeys[set] + (size_t)map * A.cap : nullptr;
         {
-            const int per = (K + nt - 1) / nt;  // <= 64 since K <= 65535
-            const int c_beg = 1 + tid * per, c_end = min(K + 1, c_beg + per);
             auto load_entry = [&](int c, uint64_t& ekey, uint32_t& zv) {
                 if (packed) {
                     const uint64_t up = T64[c] >> Gbits;  // [value 32 | ordered edge id]
@@ -776,25 +774,32 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     ekey = e.ekey; zv = e.zval;
                 }
             };
-            unsigned long long flags = 0ull;
-            for (int c = c_beg; c < c_end; ++c) {
-                uint64_t ekey; uint32_t zv;
-                load_entry(c, ekey, zv);
-                const bool emit = ekey != kRootKey ? (uint32_t)(ekey >> 32) != zv : DIM == 0;  // essential class (H0)
-                if (emit) flags |= 1ull << (c - c_beg);
-            }
-            const int cnt = __popcll(flags);
-            int incl = cnt;
+            // rounds of up to 64 contiguous basins per thread (one 64-bit flag word); each round: flags,
+            // one block scan, append the emitting basin ids to the compact list (zvalg is free after the
+            // table was initialised)
+            const int per = min(64, (K + nt - 1) / nt);
+            int total = 0;
+            for (int c_round = 1; c_round <= K; c_round += per * nt) {
+                const int c_beg = c_round + tid * per, c_end = min(K + 1, c_beg + per);
+                unsigned long long flags = 0ull;
+                for (int c = c_beg; c < c_end; ++c) {
+                    uint64_t ekey; uint32_t zv;
+                    load_entry(c, ekey, zv);
+                    const bool emit = ekey != kRootKey ? (uint32_t)(ekey >> 32) != zv : DIM == 0;  // essential class (H0)
+                    if (emit) flags |= 1ull << (c - c_beg);
+                }
+                const int cnt = __popcll(flags);
+                int incl = cnt;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
-            if (lane == 31) s_wcnt[warp] = incl;
-            __syncthreads();
-            int slot = incl - cnt, total = 0;
-            for (int w = 0; w < kPhThreads / 32; ++w) { const int v = s_wcnt[w]; total += v; if (w < warp) slot += v; }
-            // compact list of the emitting basins (zvalg is free after the table was initialised), then
-            // a coalesced pass: record j is formed by thread j mod 1024 and written to slot j
-            for (int c = c_beg; c < c_end; ++c)
-                if ((flags >> (c - c_beg)) & 1ull) zvalg[slot++] = (uint32_t)c;
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+                __syncthreads();  // previous round's readers of s_wcnt are done
+                if (lane == 31) s_wcnt[warp] = incl;
+                __syncthreads();
+                int slot = total + incl - cnt;
+                for (int w = 0; w < kPhThreads / 32; ++w) { const int v = s_wcnt[w]; total += v; if (w < warp) slot += v; }
+                for (int c = c_beg; c < c_end; ++c)
+                    if ((flags >> (c - c_beg)) & 1ull) zvalg[slot++] = (uint32_t)c;
+            }
             __syncthreads();
             // 4 records per thread per trip, staged so that the dependent global loads
             // (basin id -> root pixel -> map values) of the 4 records overlap
