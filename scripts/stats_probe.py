@@ -46,17 +46,18 @@ def run(L, maps, dim, stats):
         res["per_map"] = {k: round(v / m, 1) for k, v in d.items()}
     return res
 
-os.environ["TL_PROFILE"] = "1"
-pred, truth = make_batch(16, 256, 256, seed=1234, device="cuda")
-P = pred.reshape(-1, 256, 256).contiguous(); T = truth.reshape(-1, 256, 256).contiguous()
-X = torch.rand((224, 256, 256), device="cuda")
-S = torch.nn.functional.avg_pool2d(torch.rand((224, 1, 768, 768), device="cuda"), 3).reshape(224, 256, 256).contiguous()
-for name in ("libtopoloss_stats.so", "libtopoloss.so"):
-    L = load(name)
-    stats = "stats" in name
-    for tag, m in (("pred", P), ("truth", T), ("iid", X), ("smooth3", S)):
-        run(L, m, 1, stats)
-        print(name, tag, "dim1", run(L, m, 1, stats), flush=True)
-    if os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "dilabhelmholtzoct_b200", name)):
-        print(name, "pred dim0", run(L, P[:64], 0, stats), flush=True)
-        print(name, "truth dim0", run(L, T[:64], 0, stats), flush=True)
+if __name__ == '__main__':
+    os.environ["TL_PROFILE"] = "1"
+    pred, truth = make_batch(16, 256, 256, seed=1234, device="cuda")
+    P = pred.reshape(-1, 256, 256).contiguous(); T = truth.reshape(-1, 256, 256).contiguous()
+    X = torch.rand((224, 256, 256), device="cuda")
+    S = torch.nn.functional.avg_pool2d(torch.rand((224, 1, 768, 768), device="cuda"), 3).reshape(224, 256, 256).contiguous()
+    for name in ("libtopoloss_stats.so", "libtopoloss.so"):
+        L = load(name)
+        stats = "stats" in name
+        for tag, m in (("pred", P), ("truth", T), ("iid", X), ("smooth3", S)):
+            run(L, m, 1, stats)
+            print(name, tag, "dim1", run(L, m, 1, stats), flush=True)
+        if os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "dilabhelmholtzoct_b200", name)):
+            print(name, "pred dim0", run(L, P[:64], 0, stats), flush=True)
+            print(name, "truth dim0", run(L, T[:64], 0, stats), flush=True)
