@@ -19,7 +19,7 @@
 
 namespace tl {
 
-constexpr int kSmallMaxRow = 4097;   // nodes per row (the previous band's last-row labels live in shared memory)
+constexpr int kSmallMaxRow = 4097;   // nodes per column (the previous band's last-column labels live in shared memory)
 constexpr uint32_t kOut16 = 0xFFFFu;
 constexpr uint64_t kRootKey = ~0ull;
 constexpr int kParBytes = 65536 * 2;
@@ -74,14 +74,17 @@ __device__ __forceinline__ bool t_cas(const TRef& T, uint32_t x, const TEntry& e
 }
 
 // elder test between basins (ids are dense in raster order of their root node)
+// `rootpix` (root node of every basin) breaks value ties when basin ids are not in raster order of
+// their roots (several bands); with a single band the ids themselves are, and rootpix is null.
 template <int DIM>
-__device__ __forceinline__ bool basin_elder(uint32_t x, uint32_t zx, uint32_t y, uint32_t zy) {
+__device__ __forceinline__ bool basin_elder(uint32_t x, uint32_t zx, uint32_t y, uint32_t zy, const uint32_t* rootpix) {
     if (DIM == 1) {
         if (x == 0u) return true;   // OUTSIDE
         if (y == 0u) return false;
-        return zx != zy ? zx < zy : x > y;  // complemented values; larger raster index = elder
     }
-    return zx != zy ? zx < zy : x < y;
+    if (zx != zy) return zx < zy;  // (complemented for H1) ordered root values
+    const uint32_t px = rootpix ? rootpix[x] : x, py = rootpix ? rootpix[y] : y;
+    return DIM == 1 ? px > py : px < py;  // H1: larger raster index = elder; H0: smaller
 }
 
 
@@ -152,7 +155,7 @@ constexpr int kRing = 64;  // edges per warp in the shared staging ring (two cp.
 // by one hop (two independent 8-byte loads in flight).
 template <int DIM>
 __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossEdge* __restrict__ elist, int beg, int end,
-                                                   uint32_t ring_s TL_SPARAM) {
+                                                   uint32_t ring_s, const uint32_t* tie_root TL_SPARAM) {
     const int lane = threadIdx.x & 31;
     const int G = T.G;
     const uint64_t root_u = ~0ull >> G;              // upper part of a live basin's entry
@@ -209,7 +212,7 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
                 } else {
                     TL_STAT(3);
                     const uint32_t zx = pk_load32(T.z_s + x * 4u), zy = pk_load32(T.z_s + y * 4u);
-                    const bool sw = basin_elder<DIM>(y, zy, x, zx);
+                    const bool sw = basin_elder<DIM>(y, zy, x, zx, tie_root);
                     const uint32_t xx = sw ? y : x, yy = sw ? x : y;  // yy: the younger representative
                     const uint64_t ey = sw ? ea : eb;
                     if (pk_cas(T.t_s + yy * 8u, ey, (su << G) | xx)) {
@@ -234,7 +237,7 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
 // step by the warp.  Per lane: (x, y) are the current nodes of the two walks, doneA/doneB tell
 // whether the representative at level skey has been reached (ea / eb hold its entry).
 template <int DIM, bool SM>
-__device__ __forceinline__ void merge_lanes(const TRef& T, const CrossEdge* __restrict__ elist, int i, int i_end TL_SPARAM) {
+__device__ __forceinline__ void merge_lanes(const TRef& T, const CrossEdge* __restrict__ elist, int i, int i_end, const uint32_t* tie_root TL_SPARAM) {
     uint32_t x = 0u, y = 0u;
     uint64_t skey = 0ull;
     TEntry ea, eb;
@@ -265,7 +268,7 @@ __device__ __forceinline__ void merge_lanes(const TRef& T, const CrossEdge* __re
                     active = false;
                 } else {
                     TL_STAT(3);
-                    const bool sw = basin_elder<DIM>(y, eb.zval, x, ea.zval);
+                    const bool sw = basin_elder<DIM>(y, eb.zval, x, ea.zval, tie_root);
                     const uint32_t xx = sw ? y : x, yy = sw ? x : y;  // yy: the younger representative
                     const TEntry ey = sw ? ea : eb;
                     TEntry want;
@@ -302,8 +305,11 @@ template <int DIM>
 struct SmallCtx {
     Geo<DIM> g;
     uint16_t* par;
-    int base;  // global id of the band's first node (ids in par[] are local to the band)
-    __device__ __forceinline__ SmallCtx(const float* f, int H, int W, uint16_t* par_) : g(f, H, W), par(par_), base(0) {}
+    // the band: columns c0 .. c0+bw-1 of every row; ids in par[] are local, r * bw + (c - c0)
+    int bw, c0, rowlen;
+    FastDiv divB;
+    __device__ __forceinline__ SmallCtx(const float* f, int H, int W, uint16_t* par_) : g(f, H, W), par(par_), bw(1), c0(0), rowlen(1), divB(1u) {}
+    __device__ __forceinline__ int glob(uint32_t xl) const { const int r = (int)divB.div(xl); return r * rowlen + c0 + (int)xl - r * bw; }
 
     __device__ __forceinline__ uint32_t find(uint32_t x) const {
         volatile uint16_t* p = par;
@@ -328,7 +334,7 @@ struct SmallCtx {
             if (x == kOut16) return true;
             if (y == kOut16) return false;
         }
-        return g.nkey(base + (int)x) < g.nkey(base + (int)y);
+        return g.nkey(glob(x)) < g.nkey(glob(y));
     }
     __device__ void union0(uint32_t a, uint32_t b) {
         for (;;) {
@@ -436,26 +442,29 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             continue;
         }
 
-        // ---- phases 1-3 run per BAND of whole node rows (<= 65535 nodes, 16-bit ids local to the band;
-        //      a 256x256 H1 map is one band).  Level-0 links never leave a band: a node whose earliest
-        //      edge crosses the band border stays the root of its sub-basin and that edge is handed to
-        //      the merge tree as an ordinary crossing edge.  This is still exact: forest paths stay
+        // ---- phases 1-3 run per BAND of whole node COLUMNS (<= 65535 nodes, 16-bit ids local to the
+        //      band; a 256x256 H1 map is one band).  Level-0 links never leave a band: a node whose
+        //      earliest edge crosses the band border stays the root of its sub-basin and that edge is
+        //      handed to the merge tree as an ordinary crossing edge.  Still exact: forest paths stay
         //      key-monotone, a sub-basin root is the eldest node of its sub-basin, and the deferred merge
-        //      has zero persistence.
+        //      has zero persistence (tests/test_algorithm_model.py runs the banded variant too).
+        //      Column bands because ties resolve vertically first (H1: the edge below is the earliest of
+        //      equal edges, H0: the edge above), so plateaus contract inside a band instead of leaving one
+        //      sub-basin per column.
         const int rowlen = DIM == 1 ? W : VW, n_rows = DIM == 1 ? H : H + 1;
         const bool alias = DIM == 1 && N == 65536;  // single band whose last pixel doubles as OUTSIDE
-        const int rows_per_band = alias ? n_rows : min(n_rows, 65535 / rowlen);
-        const FastDiv divW((uint32_t)W), divVW((uint32_t)VW);
-        uint32_t* prev_lab = reinterpret_cast<uint32_t*>(smem + kParBytes + kMaskBytes);  // labels of the previous band's last row
+        const int cols_per_band = alias ? rowlen : min(rowlen, 65535 / n_rows);
+        const bool one_band = cols_per_band >= rowlen;
+        uint32_t* prev_lab = reinterpret_cast<uint32_t*>(smem + kParBytes + kMaskBytes);  // labels of the previous band's last column
         CrossEdge* elist = S.elist + (size_t)blockIdx.x * S.e_stride;
         int cid_base = 0;  // basins found in earlier bands
-        // pick(x): far end (GLOBAL node id, -2 for OUTSIDE) of x's earliest incident edge when that
-        // edge has x's own value (else -1), and whether that far end is known to be ELDER than x from
-        // registers alone
-        auto pick = [&](int x, int& oth, bool& elder_far) {
-            oth = -1; elder_far = false;
+        // pick(r, c): step (dr, dc) to the far end of node (r,c)'s earliest incident edge when that edge
+        // has the node's own value; out = the far end is OUTSIDE; none = strict local extremum (stays a
+        // root); elder_far = the far end is known to be ELDER than the node from registers alone
+        auto pick = [&](int r, int c, int& dr, int& dc, bool& out, bool& none, bool& elder_far) {
+            dr = dc = 0; out = false; none = false; elder_far = false;
+            const int x = r * rowlen + c;
             if (DIM == 1) {
-                const int r = (int)divW.div((uint32_t)x), c = x - r * W;
                 const float fp = g.px(r, c);
                 const float fu = r == 0 ? fp : g.px(r - 1, c), fd = r == H - 1 ? fp : g.px(r + 1, c);
                 const float fl = c == 0 ? fp : g.px(r, c - 1), fr = c == W - 1 ? fp : g.px(r, c + 1);
@@ -463,46 +472,51 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 // value is fp whenever the far pixel is >= fp (or the edge is a boundary edge), and
                 // among those the bitmap position orders bottom > right > left > top
                 float fo = fp;
-                bool out = false;
                 if (r == H - 1) out = true;
-                else if (fd >= fp) { oth = x + W; fo = fd; }
+                else if (fd >= fp) { dr = 1; fo = fd; }
                 else if (c == W - 1) out = true;
-                else if (fr >= fp) { oth = x + 1; fo = fr; }
+                else if (fr >= fp) { dc = 1; fo = fr; }
                 else if (c == 0) out = true;
-                else if (fl >= fp) { oth = x - 1; fo = fl; }
+                else if (fl >= fp) { dc = -1; fo = fl; }
                 else if (r == 0) out = true;
-                else if (fu >= fp) { oth = x - W; fo = fu; }
-                // else: strict local maximum, stays a root
-                // strictly higher, OUTSIDE, or equal with a larger raster index: elder than x
-                elder_far = out || fo > fp || (fo == fp && oth > x);
-                if (out || (alias && oth == N - 1)) { oth = -2; elder_far = true; }
+                else if (fu >= fp) { dr = -1; fo = fu; }
+                else none = true;  // strict local maximum
+                // strictly higher, OUTSIDE, or equal with a larger raster index: elder than the node
+                elder_far = out || fo > fp || (fo == fp && (dr > 0 || dc > 0));
+                if (alias && !out && !none && x + dr * rowlen + dc == N - 1) { out = true; elder_far = true; }
             } else {
                 uint64_t best = ~0ull;
-                const int i = (int)divVW.div((uint32_t)x), j = x - i * VW;
-                if (i > 0) {
-                    uint64_t k = g.make_ekey(g.vedge_val(i - 1, j), (uint32_t)(2 * j + (2 * i - 1) * GW));
-                    if (k < best) { best = k; oth = x - VW; }
+                if (r > 0) {
+                    uint64_t k = g.make_ekey(g.vedge_val(r - 1, c), (uint32_t)(2 * c + (2 * r - 1) * GW));
+                    if (k < best) { best = k; dr = -1; dc = 0; }
                 }
-                if (i < H) {
-                    uint64_t k = g.make_ekey(g.vedge_val(i, j), (uint32_t)(2 * j + (2 * i + 1) * GW));
-                    if (k < best) { best = k; oth = x + VW; }
+                if (r < H) {
+                    uint64_t k = g.make_ekey(g.vedge_val(r, c), (uint32_t)(2 * c + (2 * r + 1) * GW));
+                    if (k < best) { best = k; dr = 1; dc = 0; }
                 }
-                if (j > 0) {
-                    uint64_t k = g.make_ekey(g.hedge_val(i, j - 1), (uint32_t)(2 * j - 1 + (2 * i) * GW));
-                    if (k < best) { best = k; oth = x - 1; }
+                if (c > 0) {
+                    uint64_t k = g.make_ekey(g.hedge_val(r, c - 1), (uint32_t)(2 * c - 1 + (2 * r) * GW));
+                    if (k < best) { best = k; dr = 0; dc = -1; }
                 }
-                if (j < W) {
-                    uint64_t k = g.make_ekey(g.hedge_val(i, j), (uint32_t)(2 * j + 1 + (2 * i) * GW));
-                    if (k < best) { best = k; oth = x + 1; }
+                if (c < W) {
+                    uint64_t k = g.make_ekey(g.hedge_val(r, c), (uint32_t)(2 * c + 1 + (2 * r) * GW));
+                    if (k < best) { best = k; dr = 0; dc = 1; }
                 }
+                // a vertex always has an incident edge of its own value: never `none`
             }
         };
-        for (int r0 = 0; r0 < n_rows; r0 += rows_per_band) {
-            const int r1 = min(n_rows, r0 + rows_per_band);
-            const int base = r0 * rowlen, nb = (r1 - r0) * rowlen;  // this band: global nodes base .. base+nb-1
-            cx.base = base;
-            // far end as a band-local id: kOut16 stays, nodes outside the band give -1 (no level-0 link)
-            auto local_of = [&](int oth) { return oth == -2 ? (int)kOut16 : (oth >= base && oth < base + nb) ? oth - base : -1; };
+        for (int c0 = 0; c0 < rowlen; c0 += cols_per_band) {
+            const int c1 = min(rowlen, c0 + cols_per_band), bw = c1 - c0, nb = n_rows * bw;  // this band: columns c0 .. c1-1
+            const FastDiv divB((uint32_t)bw);
+            cx.bw = bw; cx.c0 = c0; cx.rowlen = rowlen; cx.divB = divB;
+            // far end of a pick as a band-local id: kOut16 for OUTSIDE, -1 when it lies outside the band
+            // (then no level-0 link is made) or when the node is a strict extremum
+            auto far_local = [&](int xl, int c, int dr, int dc, bool out, bool none) {
+                if (none) return -1;
+                if (out) return (int)kOut16;
+                const int c2 = c + dc;
+                return (c2 < c0 || c2 >= c1) ? -1 : xl + dr * bw + dc;
+            };
             __syncthreads();
             for (int x = tid; x < 65536; x += nt) par[x] = (uint16_t)x;
             __syncthreads();
@@ -517,7 +531,12 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 for (int u = 0; u < 4; ++u) {
                     const int xl = x0 + u * nt + lane;
                     other[u] = -1; elder_far[u] = false;
-                    if (xl < nb && !(alias && xl == N - 1)) { pick(base + xl, other[u], elder_far[u]); other[u] = local_of(other[u]); }
+                    if (xl < nb && !(alias && xl == N - 1)) {
+                        const int r = (int)divB.div((uint32_t)xl), c = c0 + xl - r * bw;
+                        int dr, dc; bool out, none;
+                        pick(r, c, dr, dc, out, none, elder_far[u]);
+                        other[u] = far_local(xl, c, dr, dc, out, none);
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -535,9 +554,10 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 if (bits) {
                     const int xl = w0 * 32 + lane;
                     if ((bits >> lane) & 1u) {
-                        int oth; bool ef;
-                        pick(base + xl, oth, ef);
-                        oth = local_of(oth);
+                        const int r = (int)divB.div((uint32_t)xl), c = c0 + xl - r * bw;
+                        int dr, dc; bool out, none, ef;
+                        pick(r, c, dr, dc, out, none, ef);
+                        const int oth = far_local(xl, c, dr, dc, out, none);
                         if (oth >= 0) cx.union0((uint32_t)xl, (uint32_t)oth);
                     }
                     __syncwarp();  // reconverge: without it the lanes drift apart and replay the loop body per group
@@ -559,8 +579,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             }
             TL_PROF(2);
 
-            // ---- census: dense basin ids in raster order of the roots (bands are row ranges, so ids
-            //      stay in global raster order across bands)
+            // ---- census: dense basin ids in band-local raster order of the roots (with a single band
+            //      that is the global raster order, which then serves as the tie-break between basins)
             const int chunk = (((nb + 31) / 32) + 31) & ~31;
             const int beg = min(nb, warp * chunk), end = min(nb, beg + chunk);
             {
@@ -592,9 +612,10 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     if (lane == 0) mask[i0 >> 5] = bal;
                     if (root) {
                         const int rank = run + __popc(bal & lanemask_lt());  // 0-based inside the band
+                        const int gx = cx.glob((uint32_t)i);
                         if (cid_base + 1 + rank < (int)S.k_stride) {
-                            rootpix[cid_base + 1 + rank] = (uint32_t)(base + i);
-                            zvalg[cid_base + 1 + rank] = (uint32_t)(g.nkey(base + i) >> 32);
+                            rootpix[cid_base + 1 + rank] = (uint32_t)gx;
+                            zvalg[cid_base + 1 + rank] = (uint32_t)(g.nkey(gx) >> 32);
                         }
                         par[i] = (uint16_t)rank;
                     }
@@ -617,11 +638,11 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             TL_PROF(3);
 
             // ---- compaction: the edges that cross two basins go to a per-CTA list.  Every node owns the
-            //      edge to its left and the edge above it (H1: pixel; H0: vertex), so only the "above" edge
-            //      can cross into the previous band, whose last-row labels are kept in prev_lab; H1's last
-            //      column / row also own the boundary edges to OUTSIDE.  `pos` below is the DENSE edge id:
-            //      rank of the edge among edges in bitmap order (bitmap row pair i holds W h-edges then W+1
-            //      v-edges), order-isomorphic to the bitmap position.  2 nodes per lane per trip.
+            //      edge to its left and the edge above it (H1: pixel; H0: vertex), so only the "left" edge
+            //      can cross into the previous band, whose last-column labels are kept in prev_lab; H1's
+            //      last column / row also own the boundary edges to OUTSIDE.  `pos` below is the DENSE edge
+            //      id: rank of the edge among edges in bitmap order (bitmap row pair i holds W h-edges then
+            //      W+1 v-edges), order-isomorphic to the bitmap position.  2 nodes per lane per trip.
             auto glabel = [&](uint32_t v) { return v == kOut16 ? 0u : (uint32_t)(cid_base + 1) + v; };
             for (int x0 = warp * 32; x0 < nb; x0 += 2 * nt) {  // warp-uniform trip count
                 uint32_t lab[2], lo1[2], lo2[2];
@@ -631,16 +652,15 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     const int xl = x0 + u * nt + lane;
                     lab[u] = lo1[u] = lo2[u] = 0u; rr[u] = cc[u] = 0;
                     if (xl < nb) {
-                        const int x = base + xl;
-                        rr[u] = (int)(DIM == 1 ? divW.div((uint32_t)x) : divVW.div((uint32_t)x)); cc[u] = x - rr[u] * rowlen;
+                        rr[u] = (int)divB.div((uint32_t)xl); cc[u] = c0 + xl - rr[u] * bw;
                         lab[u] = glabel(par[xl]);
-                        const bool first_row = rr[u] == r0;
+                        const bool first_col = cc[u] == c0;
                         if (DIM == 1) {
-                            lo1[u] = cc[u] == 0 ? 0u : glabel(par[xl - 1]);                        // left v-edge
-                            lo2[u] = rr[u] == 0 ? 0u : first_row ? prev_lab[cc[u]] : glabel(par[xl - W]);  // top h-edge
+                            lo1[u] = cc[u] == 0 ? 0u : first_col ? prev_lab[rr[u]] : glabel(par[xl - 1]);  // left v-edge
+                            lo2[u] = rr[u] == 0 ? 0u : glabel(par[xl - bw]);                                // top h-edge
                         } else {
-                            lo1[u] = rr[u] == 0 ? lab[u] : first_row ? prev_lab[cc[u]] : glabel(par[xl - VW]);  // up v-edge
-                            lo2[u] = cc[u] == 0 ? lab[u] : glabel(par[xl - 1]);                    // left h-edge
+                            lo1[u] = rr[u] == 0 ? lab[u] : glabel(par[xl - bw]);                            // up v-edge
+                            lo2[u] = cc[u] == 0 ? lab[u] : first_col ? prev_lab[rr[u]] : glabel(par[xl - 1]);  // left h-edge
                         }
                     }
                 }
@@ -694,9 +714,9 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 }
             }
             __syncthreads();
-            // labels of this band's last row, for the next band's "above" edges
-            if (r1 < n_rows)
-                for (int j = tid; j < rowlen; j += nt) prev_lab[j] = glabel(par[nb - rowlen + j]);
+            // labels of this band's last column, for the next band's "left" edges
+            if (c1 < rowlen)
+                for (int r = tid; r < n_rows; r += nt) prev_lab[r] = glabel(par[r * bw + bw - 1]);
             cid_base += Kb;
             TL_PROF(6);
         }
@@ -736,16 +756,17 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         // differently long walks.
         {
             const int n_cross = s_ncross;
+            const uint32_t* tie_root = one_band ? nullptr : rootpix;
             if (packed) {  // contiguous slice per warp, edges handed to idle lanes
                 const int perw = (n_cross + (nt >> 5) - 1) / (nt >> 5);
                 const int wb = min(n_cross, warp * perw), we = min(n_cross, wb + perw);
-                merge_warpq_packed<DIM>(PK, elist, wb, we, T.s + (uint32_t)ring_off + (uint32_t)warp * kRing * 16u TL_SARG);
+                merge_warpq_packed<DIM>(PK, elist, wb, we, T.s + (uint32_t)ring_off + (uint32_t)warp * kRing * 16u, tie_root TL_SARG);
             } else {       // contiguous chunk per lane
                 const int per = (n_cross + nt - 1) / nt;
                 int i = min(n_cross, tid * per);
                 const int i_end = min(n_cross, i + per);
-                if (t_in_smem) merge_lanes<DIM, true>(T, elist, i, i_end TL_SARG);
-                else merge_lanes<DIM, false>(T, elist, i, i_end TL_SARG);
+                if (t_in_smem) merge_lanes<DIM, true>(T, elist, i, i_end, tie_root TL_SARG);
+                else merge_lanes<DIM, false>(T, elist, i, i_end, tie_root TL_SARG);
             }
         }
 #ifdef TL_STATS
