@@ -38,5 +38,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_stats() -> str:
+    """Debug build with merge event counters (-DTL_STATS); used by scripts/stats_probe.py only."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out = os.path.join(_HERE, "libtopoloss_stats.so")
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-DTL_STATS", "-o", out, os.path.join(CSRC, "topoloss_api.cu")], cwd=CSRC)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

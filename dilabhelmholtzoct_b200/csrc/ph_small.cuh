@@ -146,6 +146,20 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint2 v) {
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1,%2};" :: "r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.volatile.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 constexpr int kRing = 64;  // edges per warp in the shared staging ring (two cp.async batches of 32)
 
 // Lock-free Merge of the warp's slice elist[beg..end) as a warp-synchronous state machine.
@@ -388,9 +402,13 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         const Geo<DIM>& g = cx.g;
         const int NN = g.NN, GW = g.GW, VW = g.VW;
 
+        // fast front end (H1, one band, rows of whole 128-bit quads): phases 0-3 and the compaction run
+        // on 4 consecutive pixels per lane, see below; every other shape takes the generic banded path
+        const bool fast = DIM == 1 && N <= 65536 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(g.f) & 15) == 0;
+
         // ---- phase 0: init, argmax (H0), and the constant-map shortcut (absent classes give all-zero
         //      ground-truth maps: no finite pair; H0 keeps only the essential class (0 -> argmax = 0))
-        {
+        if (!fast) {
             unsigned long long best = 0ull;
             uint32_t lo = 0xFFFFFFFFu, hi = 0u;
             if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.f) & 15) == 0) {
@@ -425,8 +443,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             if (DIM == 0) atomicMax(&s_argmax, best);
         }
         __syncthreads();
-        TL_PROF(0);
-        if (s_lo == s_hi) {  // block-uniform
+        if (!fast) TL_PROF(0);
+        if (!fast && s_lo == s_hi) {  // block-uniform
             if (tid == 0) {
                 int cnt = 0;
                 if (DIM == 0 && A.cap > 0) {
@@ -505,6 +523,263 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 // a vertex always has an incident edge of its own value: never `none`
             }
         };
+        if (fast) {
+            // ================= fast front end =================
+            // Every warp owns a contiguous chunk of whole 128-node groups; per trip a lane owns the 4
+            // consecutive pixels x .. x+3 of one row (W % 4 == 0), so the map is read with 128-bit loads
+            // (own row, row above, row below + the two scalars left / right of the quad) and par[] is
+            // read and written 4 entries (8 bytes) at a time.  The same ownership is kept through
+            // level 0, flatten, census and labelling, so root flags stay in registers.
+            const float* __restrict__ f = g.f;
+            const FastDiv divW((uint32_t)W);
+            const int chunk = ((N + 32 * 128 - 1) / (32 * 128)) * 128;  // nodes per warp
+            const int wbeg = min(N, warp * chunk), wend = min(N, wbeg + chunk);
+            const int trips = (wend - wbeg + 127) >> 7;                  // <= 16
+            cx.bw = W; cx.c0 = 0; cx.rowlen = W; cx.divB = divW;
+            if (tid == 0) par[kOut16] = (uint16_t)kOut16;  // OUTSIDE's own entry (alias: the last pixel)
+            // ---- level 0a: pick pointers, min / max of the map, tie flags for level 0b
+            {
+                float vlo = __int_as_float(0x7F800000), vhi = __int_as_float(0xFF800000);
+                for (int t = 0; t < trips; ++t) {
+                    const int x = wbeg + t * 128 + lane * 4;
+                    unsigned defer = 0u;
+                    if (x < wend) {
+                        const int r = (int)divW.div((uint32_t)x), c = x - r * W;
+                        const float4 M = __ldg(reinterpret_cast<const float4*>(f + x));
+                        const float4 U = r > 0 ? __ldg(reinterpret_cast<const float4*>(f + x - W)) : M;
+                        const float4 D = r < H - 1 ? __ldg(reinterpret_cast<const float4*>(f + x + W)) : M;
+                        const float L = c > 0 ? __ldg(f + x - 1) : 0.f;
+                        const float R = c + 4 < W ? __ldg(f + x + 4) : 0.f;
+                        vlo = fminf(vlo, fminf(fminf(M.x, M.y), fminf(M.z, M.w)));
+                        vhi = fmaxf(vhi, fmaxf(fmaxf(M.x, M.y), fmaxf(M.z, M.w)));
+                        const float m[6] = {L, M.x, M.y, M.z, M.w, R};
+                        const float u[4] = {U.x, U.y, U.z, U.w}, d[4] = {D.x, D.y, D.z, D.w};
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // earliest incident edge of the descending scan among the edges that carry the
+                            // pixel's own value: bottom > right > left > top by bitmap position; a far end that
+                            // is higher, OUTSIDE, or equal with a larger raster index is elder: plain pointer
+                            const float fp = m[k + 1];
+                            const int xk = x + k;
+                            uint32_t tgt = (uint32_t)xk;
+                            bool direct = true;
+                            if (r == H - 1) tgt = kOut16;
+                            else if (d[k] >= fp) tgt = (uint32_t)(xk + W);
+                            else if (c + k == W - 1) tgt = kOut16;
+                            else if (m[k + 2] >= fp) tgt = (uint32_t)(xk + 1);
+                            else if (c + k == 0) tgt = kOut16;
+                            else if (m[k] >= fp) { tgt = (uint32_t)(xk - 1); direct = m[k] > fp; }
+                            else if (r == 0) tgt = kOut16;
+                            else if (u[k] >= fp) { tgt = (uint32_t)(xk - W); direct = u[k] > fp; }
+                            if (alias && xk == N - 1) { tgt = kOut16; direct = true; }  // the pixel that doubles as OUTSIDE keeps itself
+                            if (!direct) { defer |= 1u << k; tgt = (uint32_t)xk; }
+                            pk[k] = tgt;
+                        }
+                        *reinterpret_cast<uint2*>(par + x) = make_uint2(pk[0] | (pk[1] << 16), pk[2] | (pk[3] << 16));
+                    }
+                    // tie flags in node order: 4 words per trip
+                    if (wbeg + t * 128 < wend) {
+                        const unsigned any = __ballot_sync(0xFFFFFFFFu, defer != 0u);
+                        unsigned v = 0u;
+                        if (any) {
+                            v = defer << (4 * (lane & 7));
+                            v |= __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+                            v |= __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+                            v |= __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+                        }
+                        if ((lane & 7) == 0) mask[((wbeg + t * 128) >> 5) + (lane >> 3)] = v;
+                    }
+                }
+                // constant-map shortcut (absent classes give all-zero ground-truth maps: no finite pair)
+                const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, mono32(vlo)), hi = __reduce_max_sync(0xFFFFFFFFu, mono32(vhi));
+                if (lane == 0 && wbeg < wend) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+            }
+            __syncthreads();
+            if (s_lo == s_hi) {  // block-uniform
+                if (tid == 0) A.counts[set][map] = 0;
+                TL_PROF(0);
+                continue;
+            }
+            // ---- level 0b: elder-linked lock-free unions for the tie-flagged nodes
+            for (int w0 = warp; w0 < ((N + 31) >> 5); w0 += nt >> 5) {
+                const unsigned bits = mask[w0];
+                if (bits) {
+                    const int xl = w0 * 32 + lane;
+                    if ((bits >> lane) & 1u) {
+                        const int r = (int)divW.div((uint32_t)xl), c = xl - r * W;
+                        int dr, dc; bool out, none, ef;
+                        pick(r, c, dr, dc, out, none, ef);
+                        if (!none) cx.union0((uint32_t)xl, out ? kOut16 : (uint32_t)(xl + dr * W + dc));
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            TL_PROF(1);
+            // ---- flatten by pointer jumping, 4 own entries per trip; a node is finished once its parent
+            //      is a root (roots are final after level 0), finished quads are skipped
+            unsigned long long rootbits = 0ull, donebits = 0ull;
+            const uint32_t par_s = (uint32_t)__cvta_generic_to_shared(par);
+            for (int round = 0;; ++round) {
+                int pending = 0;
+                for (int t = 0; t < trips; ++t) {
+                    const int x = wbeg + t * 128 + lane * 4;
+                    const bool act = x < wend && ((donebits >> (4 * t)) & 15ull) != 15ull;
+                    if (!__any_sync(0xFFFFFFFFu, act)) continue;
+                    if (act) {
+                        const uint2 w = lds_v2(par_s + 2u * (uint32_t)x);
+                        const uint32_t p0 = w.x & 0xFFFFu, p1 = w.x >> 16, p2 = w.y & 0xFFFFu, p3 = w.y >> 16;
+                        const uint32_t g0 = lds_u16(par_s + 2u * p0), g1 = lds_u16(par_s + 2u * p1), g2 = lds_u16(par_s + 2u * p2), g3 = lds_u16(par_s + 2u * p3);
+                        if (round == 0) {
+                            const unsigned rb = (p0 == (uint32_t)x ? 1u : 0u) | (p1 == (uint32_t)x + 1u ? 2u : 0u) |
+                                                (p2 == (uint32_t)x + 2u ? 4u : 0u) | (p3 == (uint32_t)x + 3u ? 8u : 0u);
+                            rootbits |= (unsigned long long)rb << (4 * t);
+                        }
+                        const unsigned dn = (g0 == p0 ? 1u : 0u) | (g1 == p1 ? 2u : 0u) | (g2 == p2 ? 4u : 0u) | (g3 == p3 ? 8u : 0u);
+                        donebits |= (unsigned long long)dn << (4 * t);
+                        if (dn != 15u) {
+                            sts_v2(par_s + 2u * (uint32_t)x, make_uint2(g0 | (g1 << 16), g2 | (g3 << 16)));
+                            pending = 1;
+                        }
+                    }
+                }
+                if (!__syncthreads_or(pending)) break;
+            }
+            if (alias && wend == N && lane == 31) rootbits &= ~(8ull << (4 * (trips - 1)));  // node N-1 is OUTSIDE, not a basin
+            TL_PROF(2);
+            // ---- census: dense basin ids in raster order of the roots
+            {
+                const int cnt = __reduce_add_sync(0xFFFFFFFFu, __popcll(rootbits));
+                if (lane == 0) s_wcnt[warp] = cnt;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const int v = s_wcnt[lane];
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+                s_wcnt[lane] = incl - v;
+                if (lane == 31) s_K = incl;
+            }
+            __syncthreads();
+            {
+                int run = s_wcnt[warp];
+                for (int t = 0; t < trips; ++t) {
+                    const int x = wbeg + t * 128 + lane * 4;
+                    const unsigned nib = (unsigned)(rootbits >> (4 * t)) & 15u;
+                    const int c = __popc(nib);
+                    int incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+                    if (nib) {
+                        uint2 w = *reinterpret_cast<const uint2*>(par + x);
+                        int rank = run + incl - c;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if ((nib >> k) & 1u) {
+                                if (rank + 1 < (int)S.k_stride) {
+                                    rootpix[rank + 1] = (uint32_t)(x + k);
+                                    zvalg[rank + 1] = ~mono32(__ldg(f + x + k));
+                                }
+                                if (k == 0) w.x = (w.x & 0xFFFF0000u) | (uint32_t)rank;
+                                else if (k == 1) w.x = (w.x & 0x0000FFFFu) | ((uint32_t)rank << 16);
+                                else if (k == 2) w.y = (w.y & 0xFFFF0000u) | (uint32_t)rank;
+                                else w.y = (w.y & 0x0000FFFFu) | ((uint32_t)rank << 16);
+                                ++rank;
+                            }
+                        }
+                        *reinterpret_cast<uint2*>(par + x) = w;
+                    }
+                    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                }
+            }
+            __syncthreads();
+            // per-node label in place: basin rank, kOut16 for OUTSIDE's basin (root entries are ranks already)
+            for (int t = 0; t < trips; ++t) {
+                const int x = wbeg + t * 128 + lane * 4;
+                const unsigned nib = (unsigned)(rootbits >> (4 * t)) & 15u;
+                if (x < wend && nib != 15u) {
+                    const uint2 w = *reinterpret_cast<const uint2*>(par + x);
+                    uint32_t e[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (!((nib >> k) & 1u) && e[k] != kOut16) e[k] = par[e[k]];
+                    *reinterpret_cast<uint2*>(par + x) = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
+                }
+            }
+            __syncthreads();
+            TL_PROF(3);
+            // ---- compaction: the edges that cross two basins go to the per-CTA list.  Every pixel owns the
+            //      v-edge to its left and the h-edge above it; the last column / row also own the boundary
+            //      edges to OUTSIDE.  Dense edge ids as in the generic path.
+            for (int t = 0; t < trips; ++t) {  // warp-uniform trip count
+                const int x = wbeg + t * 128 + lane * 4;
+                const bool valid = x < wend;
+                unsigned flags = 0u;
+                uint32_t lab[5] = {0u, 0u, 0u, 0u, 0u}, ulab[4] = {0u, 0u, 0u, 0u};  // lab[0]: left of the quad
+                float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, u[4] = {0.f, 0.f, 0.f, 0.f};
+                int r = 0, c = 0;
+                if (valid) {
+                    r = (int)divW.div((uint32_t)x); c = x - r * W;
+                    auto glab = [](uint32_t v) { return v == kOut16 ? 0u : v + 1u; };
+                    const uint2 w = *reinterpret_cast<const uint2*>(par + x);
+                    lab[1] = glab(w.x & 0xFFFFu); lab[2] = glab(w.x >> 16); lab[3] = glab(w.y & 0xFFFFu); lab[4] = glab(w.y >> 16);
+                    if (c > 0) lab[0] = glab(par[x - 1]);
+                    if (r > 0) {
+                        const uint2 wu = *reinterpret_cast<const uint2*>(par + x - W);
+                        ulab[0] = glab(wu.x & 0xFFFFu); ulab[1] = glab(wu.x >> 16); ulab[2] = glab(wu.y & 0xFFFFu); ulab[3] = glab(wu.y >> 16);
+                    }
+                    const float4 M = __ldg(reinterpret_cast<const float4*>(f + x));
+                    m[1] = M.x; m[2] = M.y; m[3] = M.z; m[4] = M.w;
+                    if (c > 0) m[0] = __ldg(f + x - 1);
+                    if (r > 0) {
+                        const float4 U = __ldg(reinterpret_cast<const float4*>(f + x - W));
+                        u[0] = U.x; u[1] = U.y; u[2] = U.z; u[3] = U.w;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t own = lab[k + 1];
+                        if (lab[k] != own) flags |= 1u << (4 * k);      // left v-edge (boundary edge when c + k == 0)
+                        if (ulab[k] != own) flags |= 2u << (4 * k);     // top h-edge (boundary edge when r == 0)
+                        if (c + k == W - 1 && own != 0u) flags |= 4u << (4 * k);
+                        if (r == H - 1 && own != 0u) flags |= 8u << (4 * k);
+                    }
+                }
+                const int cnt = __popc(flags);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+                int slot = 0;
+                if (lane == 31 && incl > 0) slot = atomicAdd(&s_ncross, incl);
+                slot = __shfl_sync(0xFFFFFFFFu, slot, 31) + incl - cnt;
+                if (flags) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float fp = m[k + 1];
+                        const uint32_t own = lab[k + 1];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (flags & (1u << (4 * k + e))) {
+                                uint32_t lo, pos;
+                                float val;
+                                if (e == 0) { lo = lab[k]; pos = (uint32_t)(r * GW + W + c + k); val = c + k == 0 ? fp : fminf(m[k], fp); }
+                                else if (e == 1) { lo = ulab[k]; pos = (uint32_t)(r * GW + c + k); val = r == 0 ? fp : fminf(u[k], fp); }
+                                else if (e == 2) { lo = 0u; pos = (uint32_t)(r * GW + 2 * W); val = fp; }
+                                else { lo = 0u; pos = (uint32_t)(H * GW + c + k); val = fp; }
+                                CrossEdge ce;
+                                ce.skey = g.make_ekey(val, pos); ce.la = lo; ce.lb = own;
+                                if (slot < (int)S.e_stride) elist[slot] = ce;
+                                ++slot;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            cid_base = s_K;
+            TL_PROF(6);
+        } else
         for (int c0 = 0; c0 < rowlen; c0 += cols_per_band) {
             const int c1 = min(rowlen, c0 + cols_per_band), bw = c1 - c0, nb = n_rows * bw;  // this band: columns c0 .. c1-1
             const FastDiv divB((uint32_t)bw);

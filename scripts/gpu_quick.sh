@@ -1,0 +1,7 @@
+#!/bin/bash
+# parity tests + phase shares (quick iteration loop)
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+timeout 120 python scripts/stats_probe.py > gpurun_out/stats_probe.log 2>&1; grep -E 'dim1' gpurun_out/stats_probe.log
+timeout 120 python scripts/time_probe.py > gpurun_out/time_probe.log 2>&1; cat gpurun_out/time_probe.log
