@@ -36,7 +36,7 @@ SIGNATURES = {
 def lib() -> ctypes.CDLL:
     global _LIB
     if _LIB is None:
-        path = _build.LIB_PATH
+        path = os.environ.get("TL_LIB_PATH") or _build.LIB_PATH  # TL_LIB_PATH: a debug build of the same library
         if not os.path.exists(path):
             raise RuntimeError(
                 f"{path} is missing: build it with `python -m dilabhelmholtzoct_b200.build` "

@@ -36,7 +36,7 @@ def run(L, maps, dim, stats):
     L.tl_debug_profile(ws.data_ptr(), prof)
     res = {"ms": round(ms, 3), "pairs/map": float(counts.float().mean())}
     tot = sum(prof) or 1
-    res["phase%[init,L0,flatten,census,merge,emit,compact]"] = [round(100.0 * v / tot, 1) for v in prof][:7]
+    res["phase%[init,L0,flatten,census,merge,emit,compact,boruvka]"] = [round(100.0 * v / tot, 1) for v in prof][:8]
     res["cycles/map"] = int(tot / n)
     if stats:
         L.tl_debug_stats(out, 1)

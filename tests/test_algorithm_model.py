@@ -70,7 +70,7 @@ def _kruskal(nkey, edges):
     return out
 
 
-def _model(nkey, edges, val, rng, level0):
+def _model(nkey, edges, val, rng, level0, boruvka=0):
     n = len(nkey)
     T = [(INF, x) for x in range(n)]  # (edge at which x dies, elder target)
     if level0:
@@ -109,6 +109,34 @@ def _model(nkey, edges, val, rng, level0):
             x = T[x][1]
         return x
     es = list(edges)
+    if boruvka:
+        # elder-rule Boruvka contraction rounds on the basin graph (csrc/ph_small.cuh, boruvka_rounds):
+        # a basin whose EARLIEST incident edge leads to an elder basin dies at that edge; survivors stay
+        # roots; edges are relabelled to live ancestors and self loops dropped; the rest is merged below
+        def root0(x):
+            while T[x][0] == -INF:
+                x = T[x][1]
+            return x
+        es = [(s, root0(a), root0(b)) for s, a, b in es]
+        es = [e for e in es if e[1] != e[2]]
+        dead = set()
+        for _ in range(boruvka):
+            best = {}
+            for s, a, b in es:
+                for x, y in ((a, b), (b, a)):
+                    if x not in best or (s, y) < best[x]:
+                        best[x] = (s, y)
+            for x, (s, y) in best.items():
+                if nkey[y] < nkey[x]:  # y elder: x dies here, final entry
+                    T[x] = (s, y)
+                    dead.add(x)
+
+            def live(x):
+                while x in dead:
+                    x = T[x][1]
+                return x
+            es = [(s, live(a), live(b)) for s, a, b in es]
+            es = [e for e in es if e[1] != e[2]]
     rng.shuffle(es)  # ANY order
     for s, x, y in es:
         while True:
@@ -141,3 +169,6 @@ def test_triplet_merge_equals_kruskal_for_any_edge_order(seed):
             for level0 in (True, False):
                 got = sorted((y, s) for y, s in _model(nkey, edges, val, rng, level0) if val(s) != val(nkey[y]))
                 assert got == want, (dim, level0, f.tolist())
+            for rounds in (1, 2, 4, 50):  # contraction rounds first, lock-free merge for the rest
+                got = sorted((y, s) for y, s in _model(nkey, edges, val, rng, True, boruvka=rounds) if val(s) != val(nkey[y]))
+                assert got == want, (dim, "boruvka", rounds, f.tolist())
