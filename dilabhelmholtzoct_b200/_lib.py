@@ -29,6 +29,8 @@ SIGNATURES = {
     "tl_timing_enable": (ctypes.c_int, [ctypes.c_int]),
     "tl_timing_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "tl_debug_profile": (ctypes.c_int, [c_fp, ctypes.POINTER(ctypes.c_ulonglong)]),
+    "tl_resample_forward": (ctypes.c_int, [c_fp] + [ctypes.c_int] * 5 + [c_fp, c_fp]),
+    "tl_resample_backward": (ctypes.c_int, [c_fp, c_fp] + [ctypes.c_int] * 5 + [c_fp, c_fp]),
     "tl_wasserstein_workspace_bytes": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_size_t)]),
 }
 

@@ -12,6 +12,7 @@
 #include "match_kernel.cuh"
 #include "ph_kernel.cuh"
 #include "ph_small.cuh"
+#include "resample_kernel.cuh"
 #include "seg_sort.cuh"
 
 namespace {
@@ -426,6 +427,56 @@ int tl_wasserstein(const float* D1, const int32_t* off1, const float* D2, const 
     m.n_diag = n_diag; m.q = q; m.loss_r = 0; m.cost = cost; m.tpers = nullptr; m.match1 = match1; m.fill1 = nullptr;
     fill_match_scratch(m, ws, ov, ominv, ou, oway, opcol, oused, sc, sr);
     tl::match_kernel<<<slots, tl::kMatchThreads, 0, static_cast<cudaStream_t>(stream)>>>(m);
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+namespace {
+int resample_args(tl::ResampleArgs& a, const float* in, int n_maps, int H, int W, int S, int apply_sigmoid) {
+    if (!in) return fail(TL_ERR_ARG, "null pointer");
+    if (n_maps <= 0 || H <= 0 || W <= 0 || S <= 0) return fail(TL_ERR_ARG, "bad shape [%d,%d,%d] -> %d", n_maps, H, W, S);
+    if ((long long)n_maps * H * W >= (1ll << 40) || (long long)n_maps * S * S >= (1ll << 40)) return fail(TL_ERR_ARG, "too large");
+    a.in = in; a.out = nullptr; a.gout = nullptr; a.gin = nullptr;
+    a.n_maps = n_maps; a.H = H; a.W = W; a.S = S; a.apply_sigmoid = apply_sigmoid != 0;
+    a.sy = S > 1 ? (float)(H - 1) / (float)(S - 1) : 0.f;
+    a.sx = S > 1 ? (float)(W - 1) / (float)(S - 1) : 0.f;
+    return TL_OK;
+}
+int grid_for(long long work, int block) {
+    long long g = (work + block - 1) / block;
+    const long long cap = 148ll * 16;  // a few waves of resident CTAs on a 148-SM B200, grid-stride beyond
+    return (int)(g < 1 ? 1 : g > cap ? cap : g);
+}
+}  // namespace
+
+int tl_resample_forward(const float* in, int n_maps, int H, int W, int S, int apply_sigmoid, float* out, void* stream) {
+    tl::ResampleArgs a;
+    int rc = resample_args(a, in, n_maps, H, W, S, apply_sigmoid);
+    if (rc != TL_OK) return rc;
+    if (!out) return fail(TL_ERR_ARG, "null pointer");
+    a.out = out;
+    tl::resample_fwd_kernel<<<grid_for((long long)n_maps * S * S, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+int tl_resample_backward(const float* grad_out, const float* in, int n_maps, int H, int W, int S, int apply_sigmoid,
+                         float* grad_in, void* stream) {
+    tl::ResampleArgs a;
+    int rc = resample_args(a, in, n_maps, H, W, S, apply_sigmoid);
+    if (rc != TL_OK) return rc;
+    if (!grad_out || !grad_in) return fail(TL_ERR_ARG, "null pointer");
+    if (reinterpret_cast<uintptr_t>(grad_in) & 15) return fail(TL_ERR_ARG, "grad_in must be 16-byte aligned");
+    a.gout = grad_out; a.gin = grad_in;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long n = (long long)n_maps * H * W;
+    tl::zero_fill_kernel<<<grid_for(n >> 2, 256), 256, 0, st>>>(grad_in, n);
+    TL_CUDA(cudaGetLastError());
+    tl::resample_bwd_kernel<<<grid_for((long long)n_maps * S * S, 256), 256, 0, st>>>(a);
     TL_CUDA(cudaGetLastError());
     return TL_OK;
 }

@@ -122,6 +122,80 @@ def topo_loss(pred_obj, true_obj, lamda, interp=0, feat_d=2, loss_q=2, loss_r=Fa
     return _TopoLossFn.apply(pred, truth, lamda, feat_d, loss_q, loss_r, 0)
 
 
+class _ResampleFn(torch.autograd.Function):
+    """tl_resample_forward / tl_resample_backward: ``F.interpolate(torch.sigmoid(x) if sig else x,
+    size=(S, S), mode="bilinear", align_corners=True)`` as one gather."""
+
+    @staticmethod
+    def forward(ctx, x, S, sig):
+        lead, (H, W) = x.shape[:-2], x.shape[-2:]
+        n = 1
+        for d in lead:
+            n *= int(d)
+        dev = x.device
+        with torch.cuda.device(dev):
+            out = torch.empty(tuple(lead) + (S, S), dtype=torch.float32, device=dev)
+            rc = _lib.lib().tl_resample_forward(x.data_ptr(), n, H, W, S, int(sig), out.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "tl_resample_forward")
+        ctx.save_for_backward(x)
+        ctx.meta = (n, H, W, S, int(sig))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        n, H, W, S, sig = ctx.meta
+        dev = x.device
+        with torch.cuda.device(dev):
+            g = g.to(dtype=torch.float32).contiguous()
+            gin = torch.empty_like(x)
+            rc = _lib.lib().tl_resample_backward(g.data_ptr(), x.data_ptr(), n, H, W, S, sig, gin.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "tl_resample_backward")
+        return gin, None, None
+
+
+def resample(x: torch.Tensor, size: int, sigmoid: bool = False) -> torch.Tensor:
+    """``F.interpolate(torch.sigmoid(x) if sigmoid else x, size=(size, size), mode="bilinear",
+    align_corners=True)`` for ``[..., H, W]`` float32 CUDA tensors, fused (the sigmoid is taken of the
+    <= 4 size^2 source pixels the outputs read, not of the whole map); differentiable."""
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise ValueError("resample expects a float32 CUDA tensor (there is no CPU fallback)")
+    if x.dim() < 2 or size < 1:
+        raise ValueError("resample expects [..., H, W] and size >= 1")
+    return _ResampleFn.apply(x.contiguous(), int(size), bool(sigmoid))
+
+
+def topo_loss_from_logits(masks, gt_masks, lamda, interp=0, feat_d=2, loss_q=2, loss_r=False):
+    """The reference call site as ONE call (training_utils.py:64 / :375)::
+
+        topo_loss(torch.sigmoid(masks.float()), gt_masks.float(), lamda, interp=..., feat_d=...)
+
+    ``masks`` are the mask decoder's logits ``[B, C, H, W]``, ``gt_masks`` the ground truth.  With
+    ``interp != 0`` the sigmoid and both bilinear down-samples (topological_loss.py:33-46) run as fused
+    gathers: only the source pixels that survive the down-sample are read, and the backward writes the
+    dense logit gradient once.  Same value and gradient as the two-step form up to fp32 rounding of the
+    resample (tests/test_resample.py).
+    """
+    if lamda == 0.0:  # topological_loss.py:30-31
+        return 0.0
+    if not (torch.is_tensor(masks) and torch.is_tensor(gt_masks)):
+        raise TypeError("masks and gt_masks must be tensors")
+    if masks.shape != gt_masks.shape or masks.dim() != 4:
+        raise ValueError("expected two [B, C, H, W] tensors of the same shape")
+    if not masks.is_cuda or not gt_masks.is_cuda:
+        raise ValueError("topo_loss runs on a CUDA device only: there is no CPU fallback")
+    if feat_d not in (0, 1):
+        raise ValueError("feat_d must be 0 or 1 for 2-D maps (the reference call site uses feat_d=1)")
+    H, W = masks.shape[-2:]
+    if interp == 0 and H != W:
+        raise ValueError("non-square maps are not supported without interp (see topo_loss)")
+    S = int(interp) if interp != 0 else H
+    pred = resample(masks.float(), S, sigmoid=True)
+    truth = resample(gt_masks.detach().float(), S, sigmoid=False)
+    pred, truth = _canonical(pred, truth)
+    return _TopoLossFn.apply(pred, truth, lamda, feat_d, loss_q, loss_r, 0)
+
+
 _COPY_STREAMS = {}
 
 

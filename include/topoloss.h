@@ -134,6 +134,27 @@ int tl_debug_profile(const void* ws, unsigned long long* host_out8);
 int tl_timing_enable(int on);
 int tl_timing_read(float* ms_sum6, int* n_calls);
 
+/*
+ * F1, the step in front of the path at the reference call site
+ *   topo_loss(torch.sigmoid(masks.float()), gt_masks.float(), 0.1, feat_d=1, interp=50)
+ *       /root/reference/octsam/models/training_utils.py:64
+ * i.e. torch.sigmoid followed by F.interpolate(size=(interp, interp), mode="bilinear",
+ * align_corners=True) of /root/reference/octsam/models/topological_loss.py:33-46, fused:
+ *   out[m, oy, ox] = bilinear_{align_corners}( apply_sigmoid ? sigmoid(in[m]) : in[m] )(oy, ox)
+ * in: [n_maps][H][W] fp32 (logits when apply_sigmoid, e.g. the mask decoder output; plain maps
+ * otherwise, e.g. ground truth), out: [n_maps][S][S].  Only the <= 4 S^2 source pixels an output
+ * needs are read and passed through the sigmoid.
+ */
+int tl_resample_forward(const float* in, int n_maps, int H, int W, int S, int apply_sigmoid,
+                        float* out, void* stream);
+
+/*
+ * Backward of tl_resample_forward: grad_in[n_maps][H][W] (16-byte aligned) is fully overwritten
+ * with sum over outputs of weight * grad_out * (apply_sigmoid ? s(1-s) : 1); `in` are the forward inputs.
+ */
+int tl_resample_backward(const float* grad_out, const float* in, int n_maps, int H, int W, int S,
+                         int apply_sigmoid, float* grad_in, void* stream);
+
 /* Bytes of workspace tl_wasserstein needs. */
 int tl_wasserstein_workspace_bytes(int n_diag, int max_rows1, int max_rows2, size_t* bytes);
 
