@@ -109,9 +109,9 @@ struct __align__(16) CrossEdge {
 
 // dense edge id -> pixel that gudhi's coface walk reaches from that edge
 template <int DIM>
-__device__ __forceinline__ int edge_top_eid(const Geo<DIM>& g, uint32_t eid) {
+__device__ __forceinline__ int edge_top_eid(const Geo<DIM>& g, uint32_t eid, const FastDiv& divRW) {
     const int RW = 2 * g.W + 1;
-    const int i = (int)eid / RW, rem = (int)eid - i * RW;
+    const int i = (int)divRW.div(eid), rem = (int)eid - i * RW;
     return rem < g.W ? g.hedge_top(i, rem) : g.vedge_top(i, rem - g.W);
 }
 
@@ -160,6 +160,10 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     return v;
 }
 
+#ifndef TL_REFILL_TH
+#define TL_REFILL_TH 8
+#endif
+constexpr int kRefillIdle = TL_REFILL_TH;  // idle lanes that trigger a refill of the warp's edge slots
 constexpr int kRing = 64;  // edges per warp in the shared staging ring (two cp.async batches of 32)
 
 // Lock-free Merge of the warp's slice elist[beg..end) as a warp-synchronous state machine.
@@ -192,7 +196,8 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
         // refill in batches: hand out new edges only when a quarter of the lanes is idle (or all are),
         // so the ~45-instruction refill section is not paid on every hop
         const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
-        if ((__popc(need) >= 8 || need == 0xFFFFFFFFu) && cons < total) {
+        bool any_active = need != 0xFFFFFFFFu;  // warp-uniform
+        if ((__popc(need) >= kRefillIdle || need == 0xFFFFFFFFu) && cons < total) {
             const int want = min(__popc(need), total - cons);
             if (cons + want > avail) { cp_async_wait_all(); __syncwarp(); avail = issued; }
             const int take = min(want, avail - cons);
@@ -207,10 +212,11 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
                 TL_STAT(1);
             }
             cons += take;
+            any_active = any_active || take > 0;
             __syncwarp();  // ring slots read before they may be overwritten
             while (issued < total && issued - cons <= kRing - 32) TL_ISSUE();
         }
-        if (!__any_sync(0xFFFFFFFFu, active)) {
+        if (!any_active) {
             if (cons >= total) break;
             continue;
         }
@@ -1053,6 +1059,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
 
         // ---- emit: every thread owns a contiguous run of basins, so ONE block scan yields
         //      deterministic slots in basin (= raster) order
+        const FastDiv divRW((uint32_t)GW), divVW((uint32_t)VW);  // exact for ids < 2^22 (multiply-shift)
         PairRec* out = A.pairs[set] + (size_t)map * A.cap;
         uint64_t* skeys = A.skeys[set] ? A.skeys[set] + (size_t)map * A.cap : nullptr;
         {
@@ -1120,16 +1127,16 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     if (j >= total) continue;
                     const int x = xx4[u];
                     if (ek4[u] == kRootKey) {  // H0 essential class: paired with argmax, emitted last by gudhi
-                        g.vertex_val(x / VW, x % VW, &rec4[u].cre);
+                        { const int vi = (int)divVW.div((uint32_t)x); g.vertex_val(vi, x - vi * VW, &rec4[u].cre); }
                         rec4[u].des = (int)(0xFFFFFFFFu - (uint32_t)s_argmax);
                         sk4[u] = ~0ull;
                     } else if (DIM == 1) {
-                        rec4[u].cre = edge_top_eid<DIM>(g, (uint32_t)(~ek4[u]));
+                        rec4[u].cre = edge_top_eid<DIM>(g, (uint32_t)(~ek4[u]), divRW);
                         rec4[u].des = x;
                         sk4[u] = ((uint64_t)(~zv4[u]) << 32) | (uint32_t)x;  // death cell = square x
                     } else {
-                        g.vertex_val(x / VW, x % VW, &rec4[u].cre);
-                        rec4[u].des = edge_top_eid<DIM>(g, (uint32_t)ek4[u]);
+                        { const int vi = (int)divVW.div((uint32_t)x); g.vertex_val(vi, x - vi * VW, &rec4[u].cre); }
+                        rec4[u].des = edge_top_eid<DIM>(g, (uint32_t)ek4[u], divRW);
                         sk4[u] = ek4[u];  // death cell = edge
                     }
                 }

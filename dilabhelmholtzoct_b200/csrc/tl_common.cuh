@@ -38,7 +38,7 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
-// Exact n / d for n < 2^22, d <= 4097 via multiply-shift (magic = ceil(2^40 / d)); avoids the
+// Exact n / d for n < 2^24, d <= 8193 via multiply-shift (magic = ceil(2^40 / d)); avoids the
 // ~30-instruction integer division in the per-node / per-edge loops.
 struct FastDiv {
     uint64_t magic;

@@ -1,0 +1,58 @@
+"""F1 measurement: the reference call site  topo_loss(sigmoid(masks), gt, 0.1, feat_d=1, interp=50)
+on [64, 14, 496, 512] logits -- two-step form (torch.sigmoid + F.interpolate + topo_loss) vs the fused
+form (topo_loss_from_logits), and the resample kernels alone with their HBM figures."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import dilabhelmholtzoct_b200 as tlb
+
+
+def timeit(fn, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+B, C, H, W, S = 64, 14, 496, 512, 50
+from dilabhelmholtzoct_b200.synthetic import make_batch
+gen = torch.Generator(device="cuda").manual_seed(99)
+pred, gt = make_batch(B, H, W, seed=1234 + 6000, device="cuda")   # OCT-like layers + blobs, call-site size
+logits = torch.logit(pred.clamp(1e-6, 1 - 1e-6)).contiguous()
+del pred
+x = logits.clone().requires_grad_(True)
+
+
+def two_step():
+    x.grad = None
+    tlb.topo_loss(torch.sigmoid(x), gt, 0.1, feat_d=1, interp=S).backward()
+
+
+def fused():
+    x.grad = None
+    tlb.topo_loss_from_logits(x, gt, 0.1, feat_d=1, interp=S).backward()
+
+
+g = torch.randn((B, C, S, S), device="cuda", generator=gen)
+xs = logits.clone().requires_grad_(True)
+res = {
+    "shape": [B, C, H, W], "interp": S,
+    "two_step_ms": timeit(two_step), "fused_ms": timeit(fused),
+    "resample_fwd_pred_ms": timeit(lambda: tlb.resample(logits, S, sigmoid=True)),
+    "resample_fwd_truth_ms": timeit(lambda: tlb.resample(gt, S)),
+    "torch_sigmoid_interp_fwd_ms": timeit(lambda: torch.nn.functional.interpolate(torch.sigmoid(logits), size=(S, S), mode="bilinear", align_corners=True)),
+}
+y = tlb.resample(xs, S, sigmoid=True)
+res["resample_bwd_ms"] = timeit(lambda: torch.autograd.grad(y, xs, g, retain_graph=True))
+yt = torch.nn.functional.interpolate(torch.sigmoid(xs), size=(S, S), mode="bilinear", align_corners=True)
+res["torch_sigmoid_interp_bwd_ms"] = timeit(lambda: torch.autograd.grad(yt, xs, g, retain_graph=True))
+bytes_grad = B * C * H * W * 4
+res["resample_bwd_write_GBps"] = bytes_grad / (res["resample_bwd_ms"] * 1e-3) / 1e9
+res["dense_grad_bytes"] = bytes_grad
+print(json.dumps(res))
