@@ -107,6 +107,11 @@ struct __align__(16) CrossEdge {
     uint32_t la, lb;
 };
 
+// one 128-bit store per record (the struct assignment compiles to two 64-bit stores)
+__device__ __forceinline__ void store_edge(CrossEdge* p, uint64_t skey, uint32_t la, uint32_t lb) {
+    *reinterpret_cast<uint4*>(p) = make_uint4((uint32_t)skey, (uint32_t)(skey >> 32), la, lb);
+}
+
 // dense edge id -> pixel that gudhi's coface walk reaches from that edge
 template <int DIM>
 __device__ __forceinline__ int edge_top_eid(const Geo<DIM>& g, uint32_t eid, const FastDiv& divRW) {
@@ -143,6 +148,10 @@ __device__ __forceinline__ bool pk_cas(uint32_t addr, uint64_t expect, uint64_t 
 __device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_s), "l"(src) : "memory");
 }
+// src_bytes = 0 writes 16 zero bytes (an edge 0-0: a self loop the merge drops at once)
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_s, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst_s), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -178,15 +187,22 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
     const int G = T.G;
     const uint64_t root_u = ~0ull >> G;              // upper part of a live basin's entry
     const uint32_t lowmask = (1u << (32 - G)) - 1u;  // the ordered dense edge id fits 32 - G bits
-    const int total = end - beg;
+    // The slice is cut into 32 sub-slices of S records, lane l fetches from sub-slice l: a batch of 32 edges
+    // is 32 edges that lie S records (tens of pixels) apart, so the edges the warp works on concurrently
+    // rarely touch the same basin (neighbouring records almost always do: CAS conflicts).  The last
+    // sub-slices are padded with zero records.
+    const int real = end - beg;
+    const int S = (real + 31) >> 5;
+    const int total = S << 5;
     int cons = 0, avail = 0, issued = 0;
     uint32_t x = 0u, y = 0u;
     uint64_t su = 0ull, ea = 0ull, eb = 0ull;
     bool active = false, doneA = true, doneB = true;
 #define TL_ISSUE()                                                                              \
     do {                                                                                        \
-        const int idx_ = issued + lane;                                                         \
-        if (idx_ < total) cp_async16(ring_s + (uint32_t)(idx_ & (kRing - 1)) * 16u, elist + beg + idx_); \
+        const int idx_ = issued + lane, src_ = lane * S + (issued >> 5);                        \
+        const bool ok_ = src_ < real;                                                           \
+        if (idx_ < total) cp_async16_zfill(ring_s + (uint32_t)(idx_ & (kRing - 1)) * 16u, elist + beg + (ok_ ? src_ : 0), ok_ ? 16u : 0u); \
         cp_async_commit();                                                                      \
         issued = min(total, issued + 32);                                                       \
     } while (0)
@@ -773,9 +789,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                                 else if (e == 1) { lo = ulab[k]; pos = (uint32_t)(r * GW + c + k); val = r == 0 ? fp : fminf(u[k], fp); }
                                 else if (e == 2) { lo = 0u; pos = (uint32_t)(r * GW + 2 * W); val = fp; }
                                 else { lo = 0u; pos = (uint32_t)(H * GW + c + k); val = fp; }
-                                CrossEdge ce;
-                                ce.skey = g.make_ekey(val, pos); ce.la = lo; ce.lb = own;
-                                if (slot < (int)S.e_stride) elist[slot] = ce;
+                                if (slot < (int)S.e_stride) store_edge(elist + slot, g.make_ekey(val, pos), lo, own);
                                 ++slot;
                             }
                         }
@@ -986,9 +1000,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                                 if (k == 0) { lo = lo1[u]; pos = (uint32_t)((r - 1) * GW + W + c); val = g.vedge_val(r - 1, c); }
                                 else { lo = lo2[u]; pos = (uint32_t)(r * GW + c - 1); val = g.hedge_val(r, c - 1); }
                             }
-                            CrossEdge ce;
-                            ce.skey = g.make_ekey(val, pos); ce.la = lo; ce.lb = lab[u];
-                            if (slot < (int)S.e_stride) elist[slot] = ce;
+                            if (slot < (int)S.e_stride) store_edge(elist + slot, g.make_ekey(val, pos), lo, lab[u]);
                             ++slot;
                         }
                     }

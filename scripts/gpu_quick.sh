@@ -5,4 +5,3 @@ timeout 240 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1
 tail -4 gpurun_out/pytest_gpu.log
 timeout 90 python scripts/stats_probe.py > gpurun_out/stats_probe.log 2>&1; grep -E 'dim1' gpurun_out/stats_probe.log | grep -v smooth3
 timeout 90 python scripts/time_probe.py > gpurun_out/time_probe.log 2>&1; grep -E "^B |pairs-only|phase" gpurun_out/time_probe.log
-timeout 120 python scripts/probe_callsite.py > gpurun_out/callsite.json 2> gpurun_out/callsite.err; cat gpurun_out/callsite.json; tail -2 gpurun_out/callsite.err
