@@ -120,6 +120,24 @@ __device__ __forceinline__ int edge_top_eid(const Geo<DIM>& g, uint32_t eid, con
     return rem < g.W ? g.hedge_top(i, rem) : g.vedge_top(i, rem - g.W);
 }
 
+// same, also returning the map value at that pixel (it is one of the two values just compared)
+template <int DIM>
+__device__ __forceinline__ void edge_top_pv(const Geo<DIM>& g, uint32_t eid, const FastDiv& divRW, int& pix, float& val) {
+    const int RW = 2 * g.W + 1, W = g.W, H = g.H;
+    const int i = (int)divRW.div(eid), rem = (int)eid - i * RW;
+    if (rem < W) {  // h-edge(i, j) between pixels (i-1, j), (i, j)
+        const int j = rem;
+        if (i == 0) { pix = j; val = g.px(0, j); }
+        else if (i == H) { pix = (H - 1) * W + j; val = g.px(H - 1, j); }
+        else { const float a = g.px(i - 1, j), b = g.px(i, j); if (a <= b) { pix = (i - 1) * W + j; val = a; } else { pix = i * W + j; val = b; } }
+    } else {        // v-edge(i, j) between pixels (i, j-1), (i, j)
+        const int j = rem - W;
+        if (j == 0) { pix = i * W; val = g.px(i, 0); }
+        else if (j == W) { pix = i * W + W - 1; val = g.px(i, W - 1); }
+        else { const float a = g.px(i, j - 1), b = g.px(i, j); if (a <= b) { pix = i * W + j - 1; val = a; } else { pix = i * W + j; val = b; } }
+    }
+}
+
 // ---- packed triplet table: one 64-bit word per basin
 //   [ 32-bit ordered edge value | P-bit ordered dense edge id | G-bit target basin ],  P + G <= 32,
 // so the whole (value, position) edge key is in the word and every comparison is exact; updated
@@ -1031,8 +1049,21 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         uint64_t* T64 = reinterpret_cast<uint64_t*>(smem);
         uint32_t* Z32 = reinterpret_cast<uint32_t*>(smem + (((K + 1) * 8 + 15) & ~15));
         __syncthreads();  // every basin id has been read: the union-find storage can become the table
+        // emission scratch in shared memory (packed case): the compact list of emitting basins borrows the
+        // staging ring after the merge; the root pixel of every basin sits behind the ring when it fits
+        // (16-bit when node ids do), so the emission's dependent global loads shrink to the map values
+        const size_t rp_off = ring_off + (size_t)(kPhThreads / 32) * kRing * sizeof(CrossEdge);
+        const bool rp16 = (DIM == 1 ? N : NN) <= 65536;  // root node ids fit 16 bits
+        const bool rp_smem = packed && rp_off + (size_t)(K + 1) * (rp16 ? 2 : 4) <= (size_t)kSmallSmemBytes;
+        const bool lst_smem = packed && (size_t)K * 2 <= (size_t)(kPhThreads / 32) * kRing * sizeof(CrossEdge);
+        uint16_t* rp_s16 = reinterpret_cast<uint16_t*>(smem + rp_off);
+        uint32_t* rp_s32 = reinterpret_cast<uint32_t*>(smem + rp_off);
+        uint16_t* lst16 = reinterpret_cast<uint16_t*>(smem + ring_off);
         if (packed) {
-            for (int c = tid; c <= K; c += nt) { T64[c] = (~0ull << Gbits) | (uint32_t)c; Z32[c] = c ? zvalg[c] : 0u; }
+            for (int c = tid; c <= K; c += nt) {
+                T64[c] = (~0ull << Gbits) | (uint32_t)c; Z32[c] = c ? zvalg[c] : 0u;
+                if (rp_smem) { const uint32_t rp = c ? rootpix[c] : 0u; if (rp16) rp_s16[c] = (uint16_t)rp; else rp_s32[c] = rp; }
+            }
         } else {
             for (int c = tid; c <= K; c += nt) {
                 TEntry e;
@@ -1113,42 +1144,47 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 int slot = total + incl - cnt;
                 for (int w = 0; w < kPhThreads / 32; ++w) { const int v = s_wcnt[w]; total += v; if (w < warp) slot += v; }
                 for (int c = c_beg; c < c_end; ++c)
-                    if ((flags >> (c - c_beg)) & 1ull) zvalg[slot++] = (uint32_t)c;
+                    if ((flags >> (c - c_beg)) & 1ull) { if (lst_smem) lst16[slot] = (uint16_t)c; else zvalg[slot] = (uint32_t)c; ++slot; }
             }
             __syncthreads();
-            // 4 records per thread per trip, staged so that the dependent global loads
-            // (basin id -> root pixel -> map values) of the 4 records overlap
+            // 4 records per thread per trip, staged so that the global loads of the 4 records overlap; per
+            // record the only dependent global accesses are the two map values that decide the edge's pixel
             for (int j0 = tid; j0 < total; j0 += 4 * nt) {
                 int cc4[4], xx4[4];
                 uint64_t ek4[4];
                 uint32_t zv4[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int j = j0 + u * nt; cc4[u] = j < total ? (int)zvalg[j] : 0; }
+                for (int u = 0; u < 4; ++u) { const int j = j0 + u * nt; cc4[u] = j < total ? (lst_smem ? (int)lst16[j] : (int)zvalg[j]) : 0; }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j0 + u * nt;
                     xx4[u] = 0; ek4[u] = kRootKey; zv4[u] = 0u;
-                    if (j < total) { xx4[u] = (int)rootpix[cc4[u]]; load_entry(cc4[u], ek4[u], zv4[u]); }
+                    if (j < total) {
+                        xx4[u] = rp_smem ? (rp16 ? (int)rp_s16[cc4[u]] : (int)rp_s32[cc4[u]]) : (int)rootpix[cc4[u]];
+                        load_entry(cc4[u], ek4[u], zv4[u]);
+                    }
                 }
                 PairRec rec4[4];
                 uint64_t sk4[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j0 + u * nt;
-                    rec4[u].cre = rec4[u].des = 0; sk4[u] = 0ull;
+                    rec4[u].cre = rec4[u].des = 0; rec4[u].b = rec4[u].d = 0.f; sk4[u] = 0ull;
                     if (j >= total) continue;
                     const int x = xx4[u];
                     if (ek4[u] == kRootKey) {  // H0 essential class: paired with argmax, emitted last by gudhi
-                        { const int vi = (int)divVW.div((uint32_t)x); g.vertex_val(vi, x - vi * VW, &rec4[u].cre); }
+                        { const int vi = (int)divVW.div((uint32_t)x); rec4[u].b = g.vertex_val(vi, x - vi * VW, &rec4[u].cre); }
                         rec4[u].des = (int)(0xFFFFFFFFu - (uint32_t)s_argmax);
+                        rec4[u].d = __ldg(g.f + rec4[u].des);
                         sk4[u] = ~0ull;
                     } else if (DIM == 1) {
-                        rec4[u].cre = edge_top_eid<DIM>(g, (uint32_t)(~ek4[u]), divRW);
                         rec4[u].des = x;
+                        rec4[u].d = __ldg(g.f + x);
+                        edge_top_pv<DIM>(g, (uint32_t)(~ek4[u]), divRW, rec4[u].cre, rec4[u].b);
                         sk4[u] = ((uint64_t)(~zv4[u]) << 32) | (uint32_t)x;  // death cell = square x
                     } else {
-                        { const int vi = (int)divVW.div((uint32_t)x); g.vertex_val(vi, x - vi * VW, &rec4[u].cre); }
-                        rec4[u].des = edge_top_eid<DIM>(g, (uint32_t)ek4[u], divRW);
+                        { const int vi = (int)divVW.div((uint32_t)x); rec4[u].b = g.vertex_val(vi, x - vi * VW, &rec4[u].cre); }
+                        edge_top_pv<DIM>(g, (uint32_t)ek4[u], divRW, rec4[u].des, rec4[u].d);
                         sk4[u] = ek4[u];  // death cell = edge
                     }
                 }
@@ -1156,8 +1192,6 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 for (int u = 0; u < 4; ++u) {
                     const int j = j0 + u * nt;
                     if (j < total && j < A.cap) {
-                        rec4[u].b = __ldg(g.f + rec4[u].cre);
-                        rec4[u].d = __ldg(g.f + rec4[u].des);
                         rec4[u].tb = rec4[u].td = __int_as_float(0x7FC00000);
                         out[j] = rec4[u];
                         if (skeys) skeys[j] = sk4[u];
