@@ -52,7 +52,7 @@ if __name__ == '__main__':
     P = pred.reshape(-1, 256, 256).contiguous(); T = truth.reshape(-1, 256, 256).contiguous()
     X = torch.rand((224, 256, 256), device="cuda")
     S = torch.nn.functional.avg_pool2d(torch.rand((224, 1, 768, 768), device="cuda"), 3).reshape(224, 256, 256).contiguous()
-    for name in ("libtopoloss_stats.so", "libtopoloss.so"):
+    for name in os.environ.get("TL_PROBE_LIBS", "libtopoloss_stats.so,libtopoloss.so").split(","):
         L = load(name)
         stats = "stats" in name
         for tag, m in (("pred", P), ("truth", T), ("iid", X), ("smooth3", S)):
