@@ -102,3 +102,143 @@ __global__ void __launch_bounds__(256) resample_bwd_kernel(ResampleArgs a) {
 }
 
 }  // namespace tl
+
+// ---------------------------------------------------------------------------------------------
+// F3: SAM post-processing of the mask decoder output at the reference call site
+//
+//   masks = F.interpolate(outputs.pred_masks.squeeze(2), (1024, 1024), mode="bilinear", align_corners=False)
+//   masks = masks[..., :reshaped_h, :reshaped_w]
+//   masks = F.interpolate(masks, (orig_h, orig_w), mode="bilinear", align_corners=False)
+//       /root/reference/octsam/models/training_utils.py:57-59
+//
+// as ONE gather: an output pixel blends 4 pixels of the (never materialised) T x T intermediate, each of
+// which blends 4 source pixels -- 16 taps on the small 256 x 256 map instead of writing and re-reading a
+// [B, N, 1024, 1024] tensor.  Both stages follow ATen's upsample_bilinear2d (align_corners=False) in
+// fp32, and the intermediate values are rounded to fp32 exactly where the two-step form rounds them:
+//   scale = in / out;  src = max(0, scale * (dst + 0.5) - 0.5);  i0 = (int)src;  i1 = i0 + (i0 < in - 1)
+//   l1 = src - i0;  l0 = 1 - l1
+namespace tl {
+
+struct PostArgs {
+    const float* in;    // [n_maps][Hs][Ws]
+    float* out;         // forward: [n_maps][oh][ow]
+    const float* gout;  // backward: [n_maps][oh][ow]
+    float* gin;         // backward: [n_maps][Hs][Ws]
+    int n_maps, Hs, Ws, T, rh, rw, oh, ow;
+    float s1y, s1x;     // Hs / T, Ws / T
+    float s2y, s2x;     // rh / oh, rw / ow
+};
+
+__device__ __forceinline__ void half_pixel(float scale, int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+    l0 = 1.0f - l1;
+}
+
+__global__ void __launch_bounds__(256) postprocess_fwd_kernel(PostArgs a) {
+    const long long total = (long long)a.n_maps * a.oh * a.ow;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(o % a.ow);
+        const long long t = o / a.ow;
+        const int oy = (int)(t % a.oh);
+        const float* p = a.in + (t / a.oh) * (long long)a.Hs * a.Ws;
+        int Y[2], X[2];
+        float ly[2], lx[2];
+        half_pixel(a.s2y, oy, a.rh, Y[0], Y[1], ly[0], ly[1]);
+        half_pixel(a.s2x, ox, a.rw, X[0], X[1], lx[0], lx[1]);
+        int ar[2][2], bc[2][2];      // stage-1 source rows of Y[0], Y[1]; source columns of X[0], X[1]
+        float la[2][2], lb[2][2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            half_pixel(a.s1y, Y[k], a.Hs, ar[k][0], ar[k][1], la[k][0], la[k][1]);
+            half_pixel(a.s1x, X[k], a.Ws, bc[k][0], bc[k][1], lb[k][0], lb[k][1]);
+        }
+        float I[2][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float v00 = __ldg(p + ar[i][0] * a.Ws + bc[j][0]), v01 = __ldg(p + ar[i][0] * a.Ws + bc[j][1]);
+                const float v10 = __ldg(p + ar[i][1] * a.Ws + bc[j][0]), v11 = __ldg(p + ar[i][1] * a.Ws + bc[j][1]);
+                I[i][j] = la[i][0] * (lb[j][0] * v00 + lb[j][1] * v01) + la[i][1] * (lb[j][0] * v10 + lb[j][1] * v11);
+            }
+        a.out[o] = ly[0] * (lx[0] * I[0][0] + lx[1] * I[0][1]) + ly[1] * (lx[0] * I[1][0] + lx[1] * I[1][1]);
+    }
+}
+
+// Backward: one CTA per (map, tile of kPostTileY x kPostTileX output pixels).  The tile's source footprint
+// is a small window of the 256 x 256 map, accumulated in shared memory (shared-memory atomics) and
+// flushed with one global atomicAdd per touched source pixel: ~50x fewer global atomics than scattering
+// the 16 taps of every output pixel.
+constexpr int kPostTileY = 16, kPostTileX = 64, kPostWin = 40 * 48;  // window capacity (rows x cols) in floats
+
+__global__ void __launch_bounds__(256) postprocess_bwd_kernel(PostArgs a, int tiles_y, int tiles_x) {
+    __shared__ float win[kPostWin];
+    __shared__ int s_box[4];  // r_lo, c_lo, n_rows, n_cols of the source window
+    const long long n_tiles = (long long)a.n_maps * tiles_y * tiles_x;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x);
+        const long long t2 = tile / tiles_x;
+        const int ty = (int)(t2 % tiles_y);
+        const long long m = t2 / tiles_y;
+        const int oy0 = ty * kPostTileY, ox0 = tx * kPostTileX;
+        const int oy1 = min(a.oh, oy0 + kPostTileY) - 1, ox1 = min(a.ow, ox0 + kPostTileX) - 1;
+        if (threadIdx.x == 0) {  // source window of the tile: both stages are monotone in the index
+            int i0, i1; float l0, l1;
+            int Ylo, Yhi, Xlo, Xhi, r_lo, r_hi, c_lo, c_hi;
+            half_pixel(a.s2y, oy0, a.rh, Ylo, i1, l0, l1); half_pixel(a.s2y, oy1, a.rh, i0, Yhi, l0, l1);
+            half_pixel(a.s2x, ox0, a.rw, Xlo, i1, l0, l1); half_pixel(a.s2x, ox1, a.rw, i0, Xhi, l0, l1);
+            half_pixel(a.s1y, Ylo, a.Hs, r_lo, i1, l0, l1); half_pixel(a.s1y, Yhi, a.Hs, i0, r_hi, l0, l1);
+            half_pixel(a.s1x, Xlo, a.Ws, c_lo, i1, l0, l1); half_pixel(a.s1x, Xhi, a.Ws, i0, c_hi, l0, l1);
+            s_box[0] = r_lo; s_box[1] = c_lo; s_box[2] = r_hi - r_lo + 1; s_box[3] = c_hi - c_lo + 1;
+        }
+        __syncthreads();
+        const int r_lo = s_box[0], c_lo = s_box[1], nr = s_box[2], nc = s_box[3];
+        const bool fits = nr * nc <= kPostWin;
+        float* gin = a.gin + m * (long long)a.Hs * a.Ws;
+        if (fits) for (int i = threadIdx.x; i < nr * nc; i += blockDim.x) win[i] = 0.f;
+        __syncthreads();
+        const float* g = a.gout + m * (long long)a.oh * a.ow;
+        const int tw = ox1 - ox0 + 1, th = oy1 - oy0 + 1;
+        for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
+            const int oy = oy0 + i / tw, ox = ox0 + i % tw;
+            const float go = __ldg(g + (long long)oy * a.ow + ox);
+            if (go == 0.f) continue;
+            int Y[2], X[2];
+            float ly[2], lx[2];
+            half_pixel(a.s2y, oy, a.rh, Y[0], Y[1], ly[0], ly[1]);
+            half_pixel(a.s2x, ox, a.rw, X[0], X[1], lx[0], lx[1]);
+#pragma unroll
+            for (int iy = 0; iy < 2; ++iy) {
+                int ar[2]; float la[2];
+                half_pixel(a.s1y, Y[iy], a.Hs, ar[0], ar[1], la[0], la[1]);
+#pragma unroll
+                for (int ix = 0; ix < 2; ++ix) {
+                    int bc[2]; float lb[2];
+                    half_pixel(a.s1x, X[ix], a.Ws, bc[0], bc[1], lb[0], lb[1]);
+                    const float w = ly[iy] * lx[ix] * go;
+#pragma unroll
+                    for (int p = 0; p < 2; ++p)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const float v = w * la[p] * lb[q];
+                            if (fits) atomicAdd(&win[(ar[p] - r_lo) * nc + (bc[q] - c_lo)], v);
+                            else atomicAdd(gin + ar[p] * a.Ws + bc[q], v);
+                        }
+                }
+            }
+        }
+        __syncthreads();
+        if (fits)
+            for (int i = threadIdx.x; i < nr * nc; i += blockDim.x) {
+                const float v = win[i];
+                if (v != 0.f) atomicAdd(gin + (r_lo + i / nc) * a.Ws + c_lo + i % nc, v);
+            }
+        __syncthreads();
+    }
+}
+
+}  // namespace tl

@@ -482,3 +482,52 @@ int tl_resample_backward(const float* grad_out, const float* in, int n_maps, int
 }
 
 }  // extern "C"
+
+extern "C" {
+
+namespace {
+int post_args(tl::PostArgs& a, int n_maps, int Hs, int Ws, int T, int rh, int rw, int oh, int ow) {
+    if (n_maps <= 0 || Hs <= 0 || Ws <= 0 || T <= 0 || oh <= 0 || ow <= 0) return fail(TL_ERR_ARG, "bad shape");
+    if (rh <= 0 || rw <= 0 || rh > T || rw > T) return fail(TL_ERR_ARG, "crop [%d,%d] outside the %dx%d intermediate", rh, rw, T, T);
+    if ((long long)n_maps * oh * ow >= (1ll << 40)) return fail(TL_ERR_ARG, "too large");
+    a.in = nullptr; a.out = nullptr; a.gout = nullptr; a.gin = nullptr;
+    a.n_maps = n_maps; a.Hs = Hs; a.Ws = Ws; a.T = T; a.rh = rh; a.rw = rw; a.oh = oh; a.ow = ow;
+    a.s1y = (float)Hs / (float)T; a.s1x = (float)Ws / (float)T;
+    a.s2y = (float)rh / (float)oh; a.s2x = (float)rw / (float)ow;
+    return TL_OK;
+}
+}  // namespace
+
+int tl_postprocess_forward(const float* in, int n_maps, int Hs, int Ws, int T, int rh, int rw, int oh, int ow,
+                           float* out, void* stream) {
+    tl::PostArgs a;
+    int rc = post_args(a, n_maps, Hs, Ws, T, rh, rw, oh, ow);
+    if (rc != TL_OK) return rc;
+    if (!in || !out) return fail(TL_ERR_ARG, "null pointer");
+    a.in = in; a.out = out;
+    tl::postprocess_fwd_kernel<<<grid_for((long long)n_maps * oh * ow, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+int tl_postprocess_backward(const float* grad_out, int n_maps, int Hs, int Ws, int T, int rh, int rw, int oh, int ow,
+                            float* grad_in, void* stream) {
+    tl::PostArgs a;
+    int rc = post_args(a, n_maps, Hs, Ws, T, rh, rw, oh, ow);
+    if (rc != TL_OK) return rc;
+    if (!grad_out || !grad_in) return fail(TL_ERR_ARG, "null pointer");
+    if (reinterpret_cast<uintptr_t>(grad_in) & 15) return fail(TL_ERR_ARG, "grad_in must be 16-byte aligned");
+    a.gout = grad_out; a.gin = grad_in;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long n = (long long)n_maps * Hs * Ws;
+    tl::zero_fill_kernel<<<grid_for(n >> 2, 256), 256, 0, st>>>(grad_in, n);
+    TL_CUDA(cudaGetLastError());
+    const int tiles_y = (oh + tl::kPostTileY - 1) / tl::kPostTileY, tiles_x = (ow + tl::kPostTileX - 1) / tl::kPostTileX;
+    const long long n_tiles = (long long)n_maps * tiles_y * tiles_x;
+    const long long cap = 148ll * 32;
+    tl::postprocess_bwd_kernel<<<(int)(n_tiles < cap ? n_tiles : cap), 256, 0, st>>>(a, tiles_y, tiles_x);
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+}  // extern "C"

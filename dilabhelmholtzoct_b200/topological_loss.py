@@ -165,6 +165,52 @@ def resample(x: torch.Tensor, size: int, sigmoid: bool = False) -> torch.Tensor:
     return _ResampleFn.apply(x.contiguous(), int(size), bool(sigmoid))
 
 
+class _PostprocessFn(torch.autograd.Function):
+    """tl_postprocess_forward / tl_postprocess_backward."""
+
+    @staticmethod
+    def forward(ctx, x, T, rh, rw, oh, ow):
+        lead, (Hs, Ws) = x.shape[:-2], x.shape[-2:]
+        n = 1
+        for d in lead:
+            n *= int(d)
+        dev = x.device
+        with torch.cuda.device(dev):
+            out = torch.empty(tuple(lead) + (oh, ow), dtype=torch.float32, device=dev)
+            rc = _lib.lib().tl_postprocess_forward(x.data_ptr(), n, Hs, Ws, T, rh, rw, oh, ow, out.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "tl_postprocess_forward")
+        ctx.meta = (tuple(x.shape), n, Hs, Ws, T, rh, rw, oh, ow)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, n, Hs, Ws, T, rh, rw, oh, ow = ctx.meta
+        dev = g.device
+        with torch.cuda.device(dev):
+            g = g.to(dtype=torch.float32).contiguous()
+            gin = torch.empty(shape, dtype=torch.float32, device=dev)
+            rc = _lib.lib().tl_postprocess_backward(g.data_ptr(), n, Hs, Ws, T, rh, rw, oh, ow, gin.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "tl_postprocess_backward")
+        return gin, None, None, None, None, None
+
+
+def postprocess_masks(pred_masks: torch.Tensor, reshaped_input_size, original_size, padded_size: int = 1024) -> torch.Tensor:
+    """The SAM post-processing of the reference training step (training_utils.py:57-59) as one gather::
+
+        masks = F.interpolate(pred_masks, (1024, 1024), mode="bilinear", align_corners=False)
+        masks = masks[..., :reshaped_input_size[0], :reshaped_input_size[1]]
+        masks = F.interpolate(masks, original_size, mode="bilinear", align_corners=False)
+
+    ``pred_masks`` is ``outputs.pred_masks.squeeze(2)``, ``[..., 256, 256]`` float32 on a CUDA device.  The
+    ``[..., 1024, 1024]`` intermediate is never written; differentiable (the backward accumulates each
+    output tile's 16-tap footprint in shared memory)."""
+    if not pred_masks.is_cuda or pred_masks.dtype != torch.float32:
+        raise ValueError("postprocess_masks expects a float32 CUDA tensor (there is no CPU fallback)")
+    rh, rw = int(reshaped_input_size[0]), int(reshaped_input_size[1])
+    oh, ow = int(original_size[0]), int(original_size[1])
+    return _PostprocessFn.apply(pred_masks.contiguous(), int(padded_size), rh, rw, oh, ow)
+
+
 def topo_loss_from_logits(masks, gt_masks, lamda, interp=0, feat_d=2, loss_q=2, loss_r=False):
     """The reference call site as ONE call (training_utils.py:64 / :375)::
 

@@ -155,6 +155,21 @@ int tl_resample_forward(const float* in, int n_maps, int H, int W, int S, int ap
 int tl_resample_backward(const float* grad_out, const float* in, int n_maps, int H, int W, int S,
                          int apply_sigmoid, float* grad_in, void* stream);
 
+/*
+ * F3: SAM post-processing of the mask decoder output, fused into one gather:
+ *   m   = F.interpolate(pred_masks.squeeze(2), (T, T), mode="bilinear", align_corners=False)   T = 1024
+ *   m   = m[..., :rh, :rw]                                                  (reshaped_input_sizes)
+ *   out = F.interpolate(m, (oh, ow), mode="bilinear", align_corners=False)  (original_sizes)
+ *       /root/reference/octsam/models/training_utils.py:57-59
+ * in: [n_maps][Hs][Ws] fp32, out: [n_maps][oh][ow].  The T x T intermediate is never materialised.
+ */
+int tl_postprocess_forward(const float* in, int n_maps, int Hs, int Ws, int T, int rh, int rw,
+                           int oh, int ow, float* out, void* stream);
+
+/* Backward of tl_postprocess_forward: grad_in[n_maps][Hs][Ws] (16-byte aligned) fully overwritten. */
+int tl_postprocess_backward(const float* grad_out, int n_maps, int Hs, int Ws, int T, int rh, int rw,
+                            int oh, int ow, float* grad_in, void* stream);
+
 /* Bytes of workspace tl_wasserstein needs. */
 int tl_wasserstein_workspace_bytes(int n_diag, int max_rows1, int max_rows2, size_t* bytes);
 

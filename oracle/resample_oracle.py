@@ -65,3 +65,35 @@ def resample_backward(grad_out, x, apply_sigmoid: bool = False) -> np.ndarray:
         s = sigmoid(x).astype(np.float64)
         gin *= s * (1.0 - s)
     return gin.astype(np.float32)
+
+
+# ------------------------------------------------------------------ F3: SAM post-processing chain
+
+def _axis_half_pixel(n_in: int, n_out: int):
+    """ATen upsample_bilinear2d, align_corners=False: scale = in / out, src = max(0, scale (dst + .5) - .5)."""
+    f32 = np.float32
+    scale = f32(n_in) / f32(n_out)
+    src = (scale * (np.arange(n_out, dtype=np.float32) + f32(0.5)) - f32(0.5)).astype(np.float32)
+    src = np.maximum(src, f32(0)).astype(np.float32)
+    i0 = src.astype(np.int64)
+    i1 = i0 + (i0 < n_in - 1)
+    l1 = (src - i0.astype(np.float32)).astype(np.float32)
+    l0 = (f32(1) - l1).astype(np.float32)
+    return i0, i1, l0, l1
+
+
+def interpolate_half_pixel(x, out_h: int, out_w: int) -> np.ndarray:
+    """F.interpolate(x, (out_h, out_w), mode='bilinear', align_corners=False) on [..., H, W] float32."""
+    x = np.asarray(x, dtype=np.float32)
+    H, W = x.shape[-2:]
+    y0, y1, ly0, ly1 = _axis_half_pixel(H, out_h)
+    x0, x1, lx0, lx1 = _axis_half_pixel(W, out_w)
+    ly0, ly1 = ly0[:, None], ly1[:, None]
+    top = lx0 * x[..., y0, :][..., :, x0] + lx1 * x[..., y0, :][..., :, x1]
+    bot = lx0 * x[..., y1, :][..., :, x0] + lx1 * x[..., y1, :][..., :, x1]
+    return (ly0 * top + ly1 * bot).astype(np.float32)
+
+
+def postprocess(x, T: int, rh: int, rw: int, oh: int, ow: int) -> np.ndarray:
+    """training_utils.py:57-59: upsample to T x T, crop to [rh, rw], resample to [oh, ow]."""
+    return interpolate_half_pixel(interpolate_half_pixel(x, T, T)[..., :rh, :rw], oh, ow)

@@ -52,6 +52,29 @@ y = tlb.resample(xs, S, sigmoid=True)
 res["resample_bwd_ms"] = timeit(lambda: torch.autograd.grad(y, xs, g, retain_graph=True))
 yt = torch.nn.functional.interpolate(torch.sigmoid(xs), size=(S, S), mode="bilinear", align_corners=True)
 res["torch_sigmoid_interp_bwd_ms"] = timeit(lambda: torch.autograd.grad(yt, xs, g, retain_graph=True))
+# ---- F3: SAM post-processing chain 256x256 -> 1024x1024 -> crop 992x1024 -> 496x512 (training_utils.py:57-59)
+import torch.nn.functional as F
+pm = torch.randn((B, C, 256, 256), device="cuda", generator=gen)
+gm = torch.randn((B, C, H, W), device="cuda", generator=gen)
+
+
+def torch_chain(t):
+    m = F.interpolate(t, (1024, 1024), mode="bilinear", align_corners=False)
+    m = m[..., :992, :1024]
+    return F.interpolate(m, (H, W), mode="bilinear", align_corners=False)
+
+
+pa = pm.clone().requires_grad_(True)
+pb = pm.clone().requires_grad_(True)
+res["postprocess_fwd_ms"] = timeit(lambda: tlb.postprocess_masks(pm, (992, 1024), (H, W)))
+res["torch_postprocess_fwd_ms"] = timeit(lambda: torch_chain(pm))
+ya = tlb.postprocess_masks(pa, (992, 1024), (H, W))
+res["postprocess_bwd_ms"] = timeit(lambda: torch.autograd.grad(ya, pa, gm, retain_graph=True))
+yb = torch_chain(pb)
+res["torch_postprocess_bwd_ms"] = timeit(lambda: torch.autograd.grad(yb, pb, gm, retain_graph=True))
+del yb
+res["postprocess_fwd_GBps"] = (B * C * (256 * 256 + H * W) * 4) / (res["postprocess_fwd_ms"] * 1e-3) / 1e9   # read source + write output
+res["postprocess_bwd_GBps"] = (B * C * (256 * 256 + H * W) * 4) / (res["postprocess_bwd_ms"] * 1e-3) / 1e9   # read grad_out + write grad_in
 bytes_grad = B * C * H * W * 4
 res["resample_bwd_write_GBps"] = bytes_grad / (res["resample_bwd_ms"] * 1e-3) / 1e9
 res["dense_grad_bytes"] = bytes_grad

@@ -118,3 +118,42 @@ def test_gpu_fused_callsite_equals_two_step_form():
     ld.backward(); le.backward()
     assert abs(float(ld) - float(le)) <= 1e-5 * abs(float(le))
     assert float((d.grad - e.grad).abs().max()) <= 1e-4 * float(e.grad.abs().max())
+
+
+# ------------------------------------------------------------------ F3: SAM post-processing chain
+
+def _torch_chain(x, T, rh, rw, oh, ow):
+    m = F.interpolate(x, (T, T), mode="bilinear", align_corners=False)
+    m = m[..., :rh, :rw]
+    return F.interpolate(m, (oh, ow), mode="bilinear", align_corners=False)
+
+
+@pytest.mark.parametrize("Hs,T,rh,rw,oh,ow", [(16, 64, 62, 64, 31, 32), (8, 32, 32, 20, 50, 33), (12, 24, 24, 24, 7, 9)])
+def test_postprocess_oracle_matches_pytorch_cpu(Hs, T, rh, rw, oh, ow):
+    rng = np.random.default_rng(Hs + T + oh)
+    x = (2.0 * rng.standard_normal((2, 3, Hs, Hs))).astype(np.float32)
+    want = _torch_chain(torch.from_numpy(x), T, rh, rw, oh, ow).numpy()
+    got = ro.postprocess(x, T, rh, rw, oh, ow)
+    assert np.abs(got - want).max() <= FWD_TOL * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Hs,T,rh,rw,oh,ow,n", [(256, 1024, 992, 1024, 496, 512, 6), (64, 256, 256, 200, 300, 123, 4),
+                                               (32, 64, 64, 64, 700, 650, 2), (16, 64, 62, 64, 31, 32, 5)])
+def test_gpu_postprocess_matches_torch_and_oracle(Hs, T, rh, rw, oh, ow, n):
+    """Forward against the oracle and torch's two-step chain on the GPU; backward against torch autograd
+    (the third case up-samples, so the backward's shared-memory window falls back to global atomics)."""
+    import dilabhelmholtzoct_b200 as tlb
+    gen = torch.Generator(device="cuda").manual_seed(Hs + oh)
+    x = 3.0 * torch.randn((n, Hs, Hs), device="cuda", generator=gen)
+    g = torch.randn((n, oh, ow), device="cuda", generator=gen)
+    a = x.clone().requires_grad_(True)
+    b = x.clone().requires_grad_(True)
+    ya = tlb.postprocess_masks(a, (rh, rw), (oh, ow), padded_size=T)
+    yb = _torch_chain(b[None], T, rh, rw, oh, ow)[0]
+    ya.backward(g)
+    yb.backward(g)
+    scale = max(1.0, float(yb.abs().max()))
+    assert float((ya - yb).abs().max()) <= FWD_TOL * scale
+    assert np.abs(ya.detach().cpu().numpy() - ro.postprocess(x.cpu().numpy(), T, rh, rw, oh, ow)).max() <= FWD_TOL * scale
+    assert float((a.grad - b.grad).abs().max()) <= BWD_TOL * float(b.grad.abs().max())
