@@ -138,34 +138,58 @@ __device__ __forceinline__ void half_pixel(float scale, int dst, int in_size, in
     l0 = 1.0f - l1;
 }
 
-__global__ void __launch_bounds__(256) postprocess_fwd_kernel(PostArgs a) {
-    const long long total = (long long)a.n_maps * a.oh * a.ow;
-    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
-        const int ox = (int)(o % a.ow);
-        const long long t = o / a.ow;
-        const int oy = (int)(t % a.oh);
-        const float* p = a.in + (t / a.oh) * (long long)a.Hs * a.Ws;
-        int Y[2], X[2];
-        float ly[2], lx[2];
-        half_pixel(a.s2y, oy, a.rh, Y[0], Y[1], ly[0], ly[1]);
-        half_pixel(a.s2x, ox, a.rw, X[0], X[1], lx[0], lx[1]);
-        int ar[2][2], bc[2][2];      // stage-1 source rows of Y[0], Y[1]; source columns of X[0], X[1]
-        float la[2][2], lb[2][2];
+// One thread per output COLUMN of a kFwdCols x kFwdRows tile: the column's taps (second-stage columns X0, X1
+// and their first-stage source columns and weights) are computed once and kept in registers while the thread
+// walks down the tile's rows; the rows' taps are computed once per tile by kFwdRows threads and broadcast
+// from shared memory.  Consecutive threads write consecutive columns (coalesced 128-byte stores).
+constexpr int kFwdCols = 128, kFwdRows = 16;
+
+struct RowTaps { int a[2][2]; float la[2][2]; float ly[2]; };  // source rows / weights of Y0, Y1; second-stage weights
+
+__global__ void __launch_bounds__(kFwdCols) postprocess_fwd_kernel(PostArgs a, int tiles_y, int tiles_x) {
+    __shared__ RowTaps rows[kFwdRows];
+    const long long n_tiles = (long long)a.n_maps * tiles_y * tiles_x;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x);
+        const long long t2 = tile / tiles_x;
+        const int ty = (int)(t2 % tiles_y);
+        const long long m = t2 / tiles_y;
+        const int oy0 = ty * kFwdRows, ox = tx * kFwdCols + threadIdx.x;
+        const int nrow = min(kFwdRows, a.oh - oy0);
+        __syncthreads();  // the previous tile's readers are done
+        if (threadIdx.x < nrow) {
+            RowTaps r;
+            int Y[2];
+            half_pixel(a.s2y, oy0 + threadIdx.x, a.rh, Y[0], Y[1], r.ly[0], r.ly[1]);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            half_pixel(a.s1y, Y[k], a.Hs, ar[k][0], ar[k][1], la[k][0], la[k][1]);
-            half_pixel(a.s1x, X[k], a.Ws, bc[k][0], bc[k][1], lb[k][0], lb[k][1]);
+            for (int k = 0; k < 2; ++k) half_pixel(a.s1y, Y[k], a.Hs, r.a[k][0], r.a[k][1], r.la[k][0], r.la[k][1]);
+            rows[threadIdx.x] = r;
         }
-        float I[2][2];
+        __syncthreads();
+        if (ox >= a.ow) continue;
+        int X[2], bc[2][2];
+        float lx[2], lb[2][2];
+        half_pixel(a.s2x, ox, a.rw, X[0], X[1], lx[0], lx[1]);
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+        for (int k = 0; k < 2; ++k) half_pixel(a.s1x, X[k], a.Ws, bc[k][0], bc[k][1], lb[k][0], lb[k][1]);
+        const float* p = a.in + m * (long long)a.Hs * a.Ws;
+        float* out = a.out + (m * a.oh + oy0) * (long long)a.ow + ox;
+        for (int i = 0; i < nrow; ++i) {
+            const RowTaps r = rows[i];
+            float I[2][2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const float v00 = __ldg(p + ar[i][0] * a.Ws + bc[j][0]), v01 = __ldg(p + ar[i][0] * a.Ws + bc[j][1]);
-                const float v10 = __ldg(p + ar[i][1] * a.Ws + bc[j][0]), v11 = __ldg(p + ar[i][1] * a.Ws + bc[j][1]);
-                I[i][j] = la[i][0] * (lb[j][0] * v00 + lb[j][1] * v01) + la[i][1] * (lb[j][0] * v10 + lb[j][1] * v11);
+            for (int y = 0; y < 2; ++y) {
+                const float* r0 = p + r.a[y][0] * a.Ws;
+                const float* r1 = p + r.a[y][1] * a.Ws;
+#pragma unroll
+                for (int x = 0; x < 2; ++x) {
+                    const float v00 = __ldg(r0 + bc[x][0]), v01 = __ldg(r0 + bc[x][1]);
+                    const float v10 = __ldg(r1 + bc[x][0]), v11 = __ldg(r1 + bc[x][1]);
+                    I[y][x] = r.la[y][0] * (lb[x][0] * v00 + lb[x][1] * v01) + r.la[y][1] * (lb[x][0] * v10 + lb[x][1] * v11);
+                }
             }
-        a.out[o] = ly[0] * (lx[0] * I[0][0] + lx[1] * I[0][1]) + ly[1] * (lx[0] * I[1][0] + lx[1] * I[1][1]);
+            out[(long long)i * a.ow] = r.ly[0] * (lx[0] * I[0][0] + lx[1] * I[0][1]) + r.ly[1] * (lx[0] * I[1][0] + lx[1] * I[1][1]);
+        }
     }
 }
 

@@ -505,7 +505,9 @@ int tl_postprocess_forward(const float* in, int n_maps, int Hs, int Ws, int T, i
     if (rc != TL_OK) return rc;
     if (!in || !out) return fail(TL_ERR_ARG, "null pointer");
     a.in = in; a.out = out;
-    tl::postprocess_fwd_kernel<<<grid_for((long long)n_maps * oh * ow, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    const int ftx = (ow + tl::kFwdCols - 1) / tl::kFwdCols, fty = (oh + tl::kFwdRows - 1) / tl::kFwdRows;
+    const long long f_tiles = (long long)n_maps * fty * ftx, f_cap = 148ll * 64;
+    tl::postprocess_fwd_kernel<<<(int)(f_tiles < f_cap ? f_tiles : f_cap), tl::kFwdCols, 0, static_cast<cudaStream_t>(stream)>>>(a, fty, ftx);
     TL_CUDA(cudaGetLastError());
     return TL_OK;
 }
