@@ -155,3 +155,39 @@ def test_threads_do_not_change_the_result():
     a = oracle.topo_loss(pred, truth, 0.1, feat_d=1, nthreads=1)
     b = oracle.topo_loss(pred, truth, 0.1, feat_d=1, nthreads=4)
     assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+# ---- independent pin of the filtration semantics: Betti curves from connected-component labelling
+# (scipy.ndimage.label, no union-find of ours).  gudhi's T-construction makes sublevel sets unions of CLOSED
+# pixels: components are 8-connected, holes are 4-connected components of the complement that do not touch
+# the border.  For every threshold t,
+#   beta_0(t) = #{H0 pairs: b <= t < d} (+1 for the essential class once the minimum is in)
+#   beta_1(t) = #{H1 pairs: b <= t < d}
+# must equal the component / hole counts of {f <= t}.
+@pytest.mark.parametrize("seed,levels", [(0, 0), (1, 0), (2, 6), (3, 3), (4, 2)])
+def test_betti_curves_match_connected_component_counts(seed, levels):
+    from scipy import ndimage
+    rng = np.random.default_rng(100 + seed)
+    H, W = int(rng.integers(6, 20)), int(rng.integers(6, 20))
+    H = W  # square maps only on this path
+    f = rng.random((H, W)).astype(np.float32)
+    if levels:
+        f = (np.floor(f * levels) / levels).astype(np.float32)
+    flat = f.ravel()
+    p0 = oracle.cubical_pairs(f, 0)
+    p1 = oracle.cubical_pairs(f, 1)
+    ess = p0[-1]                      # essential class last: (global-min pixel, argmax)
+    fin0 = p0[:-1]
+    assert flat[ess[0]] == f.min() and ess[1] == int(np.argmax(f))
+    eight = np.ones((3, 3), dtype=int)
+    four = ndimage.generate_binary_structure(2, 1)
+    for t in np.unique(f):
+        sub = f <= t
+        n_comp = ndimage.label(sub, structure=eight)[1]
+        lab, n_bg = ndimage.label(~sub, structure=four)
+        border = set(np.unique(np.concatenate([lab[0], lab[-1], lab[:, 0], lab[:, -1]]))) - {0}
+        n_holes = n_bg - len(border)
+        b0 = int(np.sum((flat[fin0[:, 0]] <= t) & (t < flat[fin0[:, 1]]))) + 1 if len(fin0) else 1
+        b1 = int(np.sum((flat[p1[:, 0]] <= t) & (t < flat[p1[:, 1]]))) if len(p1) else 0
+        assert b0 == n_comp, (t, b0, n_comp)
+        assert b1 == n_holes, (t, b1, n_holes)
