@@ -560,7 +560,11 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     uint64_t k = g.make_ekey(g.hedge_val(r, c), (uint32_t)(2 * c + 1 + (2 * r) * GW));
                     if (k < best) { best = k; dr = 0; dc = 1; }
                 }
-                // a vertex always has an incident edge of its own value: never `none`
+                // a vertex always has an incident edge of its own value: never `none`.  The far vertex is a
+                // face of that edge, so its value is <= the edge's = the node's own: it is elder when it
+                // comes earlier in raster order (up / left), or when its value is strictly smaller
+                if (dr < 0 || dc < 0) elder_far = true;
+                else elder_far = mono32(g.vertex_val(r + dr, c + dc, nullptr)) < (uint32_t)(best >> 32);
             }
         };
         if (fast) {
