@@ -444,11 +444,13 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
 
         // fast front end (H1, one band, rows of whole 128-bit quads): phases 0-3 and the compaction run
         // on 4 consecutive pixels per lane, see below; every other shape takes the generic banded path
-        const bool fast = DIM == 1 && N <= 65536 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(g.f) & 15) == 0;
+        // (maps with more than 65535 pixels go through it in bands of whole columns, 4-column aligned)
+        const bool fast = DIM == 1 && (W & 3) == 0 && H <= 16383 && (reinterpret_cast<uintptr_t>(g.f) & 15) == 0;
+        const bool fast_one = fast && N <= 65536;  // single band: min / max fused into level 0
 
         // ---- phase 0: init, argmax (H0), and the constant-map shortcut (absent classes give all-zero
         //      ground-truth maps: no finite pair; H0 keeps only the essential class (0 -> argmax = 0))
-        if (!fast) {
+        if (!fast_one) {
             unsigned long long best = 0ull;
             uint32_t lo = 0xFFFFFFFFu, hi = 0u;
             if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.f) & 15) == 0) {
@@ -483,8 +485,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             if (DIM == 0) atomicMax(&s_argmax, best);
         }
         __syncthreads();
-        if (!fast) TL_PROF(0);
-        if (!fast && s_lo == s_hi) {  // block-uniform
+        if (!fast_one) TL_PROF(0);
+        if (!fast_one && s_lo == s_hi) {  // block-uniform
             if (tid == 0) {
                 int cnt = 0;
                 if (DIM == 0 && A.cap > 0) {
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         //      sub-basin per column.
         const int rowlen = DIM == 1 ? W : VW, n_rows = DIM == 1 ? H : H + 1;
         const bool alias = DIM == 1 && N == 65536;  // single band whose last pixel doubles as OUTSIDE
-        const int cols_per_band = alias ? rowlen : min(rowlen, 65535 / n_rows);
+        const int cols_per_band = alias ? rowlen : fast ? min(rowlen, (65535 / n_rows) & ~3) : min(rowlen, 65535 / n_rows);
         const bool one_band = cols_per_band >= rowlen;
         uint32_t* prev_lab = reinterpret_cast<uint32_t*>(smem + kParBytes + kMaskBytes);  // labels of the previous band's last column
         CrossEdge* elist = S.elist + (size_t)blockIdx.x * S.e_stride;
@@ -574,26 +576,34 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             // (own row, row above, row below + the two scalars left / right of the quad) and par[] is
             // read and written 4 entries (8 bytes) at a time.  The same ownership is kept through
             // level 0, flatten, census and labelling, so root flags stay in registers.
+            // Maps with more than 65535 pixels are processed in bands of whole columns (a multiple of 4
+            // wide): ids in par[] are band-local, r * bw + (c - c0); level-0 links never leave a band (a
+            // pixel whose earliest edge crosses the band border stays the root of its sub-basin and the
+            // deferred zero-persistence merge goes to the merge tree), see the generic path below.
             const float* __restrict__ f = g.f;
-            const FastDiv divW((uint32_t)W);
-            const int chunk = ((N + 32 * 128 - 1) / (32 * 128)) * 128;  // nodes per warp
-            const int wbeg = min(N, warp * chunk), wend = min(N, wbeg + chunk);
+            for (int c0 = 0; c0 < W; c0 += cols_per_band) {
+            const int c1 = min(W, c0 + cols_per_band), bw = c1 - c0, nb = H * bw;  // this band: columns c0 .. c1-1
+            const FastDiv divW((uint32_t)bw);
+            const int chunk = ((nb + 32 * 128 - 1) / (32 * 128)) * 128;  // nodes per warp
+            const int wbeg = min(nb, warp * chunk), wend = min(nb, wbeg + chunk);
             const int trips = (wend - wbeg + 127) >> 7;                  // <= 16
-            cx.bw = W; cx.c0 = 0; cx.rowlen = W; cx.divB = divW;
+            cx.bw = bw; cx.c0 = c0; cx.rowlen = W; cx.divB = divW;
+            __syncthreads();  // the previous band's readers of par[] are done
             if (tid == 0) par[kOut16] = (uint16_t)kOut16;  // OUTSIDE's own entry (alias: the last pixel)
             // ---- level 0a: pick pointers, min / max of the map, tie flags for level 0b
             {
                 float vlo = __int_as_float(0x7F800000), vhi = __int_as_float(0xFF800000);
                 for (int t = 0; t < trips; ++t) {
-                    const int x = wbeg + t * 128 + lane * 4;
+                    const int x = wbeg + t * 128 + lane * 4;  // band-local id of the quad
                     unsigned defer = 0u;
                     if (x < wend) {
-                        const int r = (int)divW.div((uint32_t)x), c = x - r * W;
-                        const float4 M = __ldg(reinterpret_cast<const float4*>(f + x));
-                        const float4 U = r > 0 ? __ldg(reinterpret_cast<const float4*>(f + x - W)) : M;
-                        const float4 D = r < H - 1 ? __ldg(reinterpret_cast<const float4*>(f + x + W)) : M;
-                        const float L = c > 0 ? __ldg(f + x - 1) : 0.f;
-                        const float R = c + 4 < W ? __ldg(f + x + 4) : 0.f;
+                        const int r = (int)divW.div((uint32_t)x), cl = x - r * bw, c = c0 + cl;
+                        const float* q = f + r * W + c;
+                        const float4 M = __ldg(reinterpret_cast<const float4*>(q));
+                        const float4 U = r > 0 ? __ldg(reinterpret_cast<const float4*>(q - W)) : M;
+                        const float4 D = r < H - 1 ? __ldg(reinterpret_cast<const float4*>(q + W)) : M;
+                        const float L = c > 0 ? __ldg(q - 1) : 0.f;
+                        const float R = c + 4 < W ? __ldg(q + 4) : 0.f;
                         vlo = fminf(vlo, fminf(fminf(M.x, M.y), fminf(M.z, M.w)));
                         vhi = fmaxf(vhi, fmaxf(fmaxf(M.x, M.y), fmaxf(M.z, M.w)));
                         const float m[6] = {L, M.x, M.y, M.z, M.w, R};
@@ -603,19 +613,20 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                         for (int k = 0; k < 4; ++k) {
                             // earliest incident edge of the descending scan among the edges that carry the
                             // pixel's own value: bottom > right > left > top by bitmap position; a far end that
-                            // is higher, OUTSIDE, or equal with a larger raster index is elder: plain pointer
+                            // is higher, OUTSIDE, or equal with a larger raster index is elder: plain pointer;
+                            // a far end in another band: no link (the pixel stays a sub-basin root)
                             const float fp = m[k + 1];
                             const int xk = x + k;
                             uint32_t tgt = (uint32_t)xk;
                             bool direct = true;
                             if (r == H - 1) tgt = kOut16;
-                            else if (d[k] >= fp) tgt = (uint32_t)(xk + W);
+                            else if (d[k] >= fp) tgt = (uint32_t)(xk + bw);
                             else if (c + k == W - 1) tgt = kOut16;
-                            else if (m[k + 2] >= fp) tgt = (uint32_t)(xk + 1);
+                            else if (m[k + 2] >= fp) { if (cl + k + 1 < bw) tgt = (uint32_t)(xk + 1); }
                             else if (c + k == 0) tgt = kOut16;
-                            else if (m[k] >= fp) { tgt = (uint32_t)(xk - 1); direct = m[k] > fp; }
+                            else if (m[k] >= fp) { if (cl + k > 0) { tgt = (uint32_t)(xk - 1); direct = m[k] > fp; } }
                             else if (r == 0) tgt = kOut16;
-                            else if (u[k] >= fp) { tgt = (uint32_t)(xk - W); direct = u[k] > fp; }
+                            else if (u[k] >= fp) { tgt = (uint32_t)(xk - bw); direct = u[k] > fp; }
                             if (alias && xk == N - 1) { tgt = kOut16; direct = true; }  // the pixel that doubles as OUTSIDE keeps itself
                             if (!direct) { defer |= 1u << k; tgt = (uint32_t)xk; }
                             pk[k] = tgt;
@@ -635,26 +646,26 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                         if ((lane & 7) == 0) mask[((wbeg + t * 128) >> 5) + (lane >> 3)] = v;
                     }
                 }
-                // constant-map shortcut (absent classes give all-zero ground-truth maps: no finite pair)
-                const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, mono32(vlo)), hi = __reduce_max_sync(0xFFFFFFFFu, mono32(vhi));
-                if (lane == 0 && wbeg < wend) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+                // constant-map shortcut (absent classes give all-zero ground-truth maps: no finite pair);
+                // banded maps took it in phase 0
+                if (fast_one) {
+                    const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, mono32(vlo)), hi = __reduce_max_sync(0xFFFFFFFFu, mono32(vhi));
+                    if (lane == 0 && wbeg < wend) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+                }
             }
             __syncthreads();
-            if (s_lo == s_hi) {  // block-uniform
-                if (tid == 0) A.counts[set][map] = 0;
-                TL_PROF(0);
-                continue;
-            }
+            if (fast_one && s_lo == s_hi) break;  // block-uniform: constant map, handled after the band loop
             // ---- level 0b: elder-linked lock-free unions for the tie-flagged nodes
-            for (int w0 = warp; w0 < ((N + 31) >> 5); w0 += nt >> 5) {
+            for (int w0 = warp; w0 < ((nb + 31) >> 5); w0 += nt >> 5) {
                 const unsigned bits = mask[w0];
                 if (bits) {
                     const int xl = w0 * 32 + lane;
                     if ((bits >> lane) & 1u) {
-                        const int r = (int)divW.div((uint32_t)xl), c = xl - r * W;
+                        const int r = (int)divW.div((uint32_t)xl), c = c0 + xl - r * bw;
                         int dr, dc; bool out, none, ef;
                         pick(r, c, dr, dc, out, none, ef);
-                        if (!none) cx.union0((uint32_t)xl, out ? kOut16 : (uint32_t)(xl + dr * W + dc));
+                        if (!none && (out || (c + dc >= c0 && c + dc < c1)))
+                            cx.union0((uint32_t)xl, out ? kOut16 : (uint32_t)(xl + dr * bw + dc));
                     }
                     __syncwarp();
                 }
@@ -692,7 +703,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             }
             if (alias && wend == N && lane == 31) rootbits &= ~(8ull << (4 * (trips - 1)));  // node N-1 is OUTSIDE, not a basin
             TL_PROF(2);
-            // ---- census: dense basin ids in raster order of the roots
+            // ---- census: dense basin ids in (band-local) raster order of the roots
             {
                 const int cnt = __reduce_add_sync(0xFFFFFFFFu, __popcll(rootbits));
                 if (lane == 0) s_wcnt[warp] = cnt;
@@ -707,6 +718,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 if (lane == 31) s_K = incl;
             }
             __syncthreads();
+            const int Kb = s_K;  // basins of this band: global ids cid_base+1 .. cid_base+Kb
             {
                 int run = s_wcnt[warp];
                 for (int t = 0; t < trips; ++t) {
@@ -718,13 +730,14 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
                     if (nib) {
                         uint2 w = *reinterpret_cast<const uint2*>(par + x);
-                        int rank = run + incl - c;
+                        int rank = run + incl - c;  // 0-based inside the band
+                        const int r = (int)divW.div((uint32_t)x), gx = r * W + c0 + x - r * bw;  // global pixel of the quad
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if ((nib >> k) & 1u) {
-                                if (rank + 1 < (int)S.k_stride) {
-                                    rootpix[rank + 1] = (uint32_t)(x + k);
-                                    zvalg[rank + 1] = ~mono32(__ldg(f + x + k));
+                                if (cid_base + rank + 1 < (int)S.k_stride) {
+                                    rootpix[cid_base + rank + 1] = (uint32_t)(gx + k);
+                                    zvalg[cid_base + rank + 1] = ~mono32(__ldg(f + gx + k));
                                 }
                                 if (k == 0) w.x = (w.x & 0xFFFF0000u) | (uint32_t)rank;
                                 else if (k == 1) w.x = (w.x & 0x0000FFFFu) | ((uint32_t)rank << 16);
@@ -739,7 +752,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 }
             }
             __syncthreads();
-            // per-node label in place: basin rank, kOut16 for OUTSIDE's basin (root entries are ranks already)
+            // per-node label in place: band-local basin rank, kOut16 for OUTSIDE's basin (root entries are ranks already)
             for (int t = 0; t < trips; ++t) {
                 const int x = wbeg + t * 128 + lane * 4;
                 const unsigned nib = (unsigned)(rootbits >> (4 * t)) & 15u;
@@ -755,8 +768,10 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             __syncthreads();
             TL_PROF(3);
             // ---- compaction: the edges that cross two basins go to the per-CTA list.  Every pixel owns the
-            //      v-edge to its left and the h-edge above it; the last column / row also own the boundary
-            //      edges to OUTSIDE.  Dense edge ids as in the generic path.
+            //      v-edge to its left and the h-edge above it (the left edge of a band's first column reaches
+            //      into the previous band, whose last-column labels are kept in prev_lab); the last column /
+            //      row also own the boundary edges to OUTSIDE.  Dense edge ids as in the generic path.
+            auto glab = [&](uint32_t v) { return v == kOut16 ? 0u : (uint32_t)(cid_base + 1) + v; };
             for (int t = 0; t < trips; ++t) {  // warp-uniform trip count
                 const int x = wbeg + t * 128 + lane * 4;
                 const bool valid = x < wend;
@@ -765,20 +780,22 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, u[4] = {0.f, 0.f, 0.f, 0.f};
                 int r = 0, c = 0;
                 if (valid) {
-                    r = (int)divW.div((uint32_t)x); c = x - r * W;
-                    auto glab = [](uint32_t v) { return v == kOut16 ? 0u : v + 1u; };
+                    r = (int)divW.div((uint32_t)x);
+                    const int cl = x - r * bw;
+                    c = c0 + cl;
                     const uint2 w = *reinterpret_cast<const uint2*>(par + x);
                     lab[1] = glab(w.x & 0xFFFFu); lab[2] = glab(w.x >> 16); lab[3] = glab(w.y & 0xFFFFu); lab[4] = glab(w.y >> 16);
-                    if (c > 0) lab[0] = glab(par[x - 1]);
+                    if (c > 0) lab[0] = cl > 0 ? glab(par[x - 1]) : prev_lab[r];
                     if (r > 0) {
-                        const uint2 wu = *reinterpret_cast<const uint2*>(par + x - W);
+                        const uint2 wu = *reinterpret_cast<const uint2*>(par + x - bw);
                         ulab[0] = glab(wu.x & 0xFFFFu); ulab[1] = glab(wu.x >> 16); ulab[2] = glab(wu.y & 0xFFFFu); ulab[3] = glab(wu.y >> 16);
                     }
-                    const float4 M = __ldg(reinterpret_cast<const float4*>(f + x));
+                    const float* q = f + r * W + c;
+                    const float4 M = __ldg(reinterpret_cast<const float4*>(q));
                     m[1] = M.x; m[2] = M.y; m[3] = M.z; m[4] = M.w;
-                    if (c > 0) m[0] = __ldg(f + x - 1);
+                    if (c > 0) m[0] = __ldg(q - 1);
                     if (r > 0) {
-                        const float4 U = __ldg(reinterpret_cast<const float4*>(f + x - W));
+                        const float4 U = __ldg(reinterpret_cast<const float4*>(q - W));
                         u[0] = U.x; u[1] = U.y; u[2] = U.z; u[3] = U.w;
                     }
 #pragma unroll
@@ -819,8 +836,17 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 }
             }
             __syncthreads();
-            cid_base = s_K;
+            // labels of this band's last column, for the next band's "left" edges
+            if (c1 < W)
+                for (int r = tid; r < H; r += nt) prev_lab[r] = glab(par[r * bw + bw - 1]);
+            cid_base += Kb;
             TL_PROF(6);
+            }  // bands
+            if (fast_one && s_lo == s_hi) {  // block-uniform: constant map
+                if (tid == 0) A.counts[set][map] = 0;
+                TL_PROF(0);
+                continue;
+            }
         } else
         for (int c0 = 0; c0 < rowlen; c0 += cols_per_band) {
             const int c1 = min(rowlen, c0 + cols_per_band), bw = c1 - c0, nb = n_rows * bw;  // this band: columns c0 .. c1-1
