@@ -191,6 +191,10 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 #define TL_REFILL_TH 8
 #endif
 constexpr int kRefillIdle = TL_REFILL_TH;  // idle lanes that trigger a refill of the warp's edge slots
+#ifndef TL_HOPS
+#define TL_HOPS 3
+#endif
+constexpr int kHopsPerIter = TL_HOPS;
 constexpr int kRing = 64;  // edges per warp in the shared staging ring (two cp.async batches of 32)
 
 // Lock-free Merge of the warp's slice elist[beg..end) as a warp-synchronous state machine.
@@ -255,10 +259,13 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
             continue;
         }
         if (active) {
-            if (!doneA) { TL_STAT(0); ea = pk_load(T.t_s + x * 8u); }
-            if (!doneB) { TL_STAT(0); eb = pk_load(T.t_s + y * 8u); }
-            if (!doneA) { if ((ea >> G) > su) doneA = true; else x = (uint32_t)ea & T.gmask; }
-            if (!doneB) { if ((eb >> G) > su) doneB = true; else y = (uint32_t)eb & T.gmask; }
+#pragma unroll
+            for (int hop = 0; hop < kHopsPerIter; ++hop) {  // several hops per trip through the loop's vote / refill logic
+                if (!doneA) { TL_STAT(0); ea = pk_load(T.t_s + x * 8u); }
+                if (!doneB) { TL_STAT(0); eb = pk_load(T.t_s + y * 8u); }
+                if (!doneA) { if ((ea >> G) > su) doneA = true; else x = (uint32_t)ea & T.gmask; }
+                if (!doneB) { if ((eb >> G) > su) doneB = true; else y = (uint32_t)eb & T.gmask; }
+            }
             if (doneA && doneB) {
                 TL_STAT(2);
                 if (x == y) {
