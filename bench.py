@@ -132,6 +132,9 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+_SAVED_STDOUT = None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,8 +168,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version / debug lines to stdout by default: keep stdout for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its version / debug lines on stdout (fd 1) when it initialises: park fd 1 on stderr for
+        # the whole run and give it back just before the one JSON line is printed
+        sys.stdout.flush()
+        global _SAVED_STDOUT
+        _SAVED_STDOUT = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     B = args.batch
@@ -278,6 +285,9 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "masks/s", "cores": cores, "kind": "port",
                                 "sample": f"first {n} images ({n * C} maps) of the same batch, one pass, "
                                           f"oracle/topo_oracle.c with OpenMP over maps ({dt:.2f} s)"}
+    if _SAVED_STDOUT is not None:
+        sys.stdout.flush()
+        os.dup2(_SAVED_STDOUT, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
