@@ -191,6 +191,9 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 #define TL_REFILL_TH 8
 #endif
 constexpr int kRefillIdle = TL_REFILL_TH;  // idle lanes that trigger a refill of the warp's edge slots
+#ifndef TL_FLAT2
+#define TL_FLAT2 1
+#endif
 #ifndef TL_HOPS
 #define TL_HOPS 3
 #endif
@@ -692,18 +695,25 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                     if (act) {
                         const uint2 w = lds_v2(par_s + 2u * (uint32_t)x);
                         const uint32_t p0 = w.x & 0xFFFFu, p1 = w.x >> 16, p2 = w.y & 0xFFFFu, p3 = w.y >> 16;
+#if TL_FLAT2
+                        // two jumps per round (parent's parent's parent): a third fewer block-wide rounds on the long
+                        // pointer chains of plateaus
+                        const uint32_t q0 = lds_u16(par_s + 2u * p0), q1 = lds_u16(par_s + 2u * p1), q2 = lds_u16(par_s + 2u * p2), q3 = lds_u16(par_s + 2u * p3);
+                        const uint32_t g0 = lds_u16(par_s + 2u * q0), g1 = lds_u16(par_s + 2u * q1), g2 = lds_u16(par_s + 2u * q2), g3 = lds_u16(par_s + 2u * q3);
+#else
                         const uint32_t g0 = lds_u16(par_s + 2u * p0), g1 = lds_u16(par_s + 2u * p1), g2 = lds_u16(par_s + 2u * p2), g3 = lds_u16(par_s + 2u * p3);
+                        const uint32_t q0 = p0, q1 = p1, q2 = p2, q3 = p3;
+#endif
                         if (round == 0) {
                             const unsigned rb = (p0 == (uint32_t)x ? 1u : 0u) | (p1 == (uint32_t)x + 1u ? 2u : 0u) |
                                                 (p2 == (uint32_t)x + 2u ? 4u : 0u) | (p3 == (uint32_t)x + 3u ? 8u : 0u);
                             rootbits |= (unsigned long long)rb << (4 * t);
                         }
-                        const unsigned dn = (g0 == p0 ? 1u : 0u) | (g1 == p1 ? 2u : 0u) | (g2 == p2 ? 4u : 0u) | (g3 == p3 ? 8u : 0u);
+                        const unsigned dn = (g0 == q0 ? 1u : 0u) | (g1 == q1 ? 2u : 0u) | (g2 == q2 ? 4u : 0u) | (g3 == q3 ? 8u : 0u);
                         donebits |= (unsigned long long)dn << (4 * t);
-                        if (dn != 15u) {
+                        if (g0 != p0 || g1 != p1 || g2 != p2 || g3 != p3)
                             sts_v2(par_s + 2u * (uint32_t)x, make_uint2(g0 | (g1 << 16), g2 | (g3 << 16)));
-                            pending = 1;
-                        }
+                        if (dn != 15u) pending = 1;
                     }
                 }
                 if (!__syncthreads_or(pending)) break;
