@@ -52,6 +52,7 @@ struct PhArgs {
     uint64_t* T;            // [gridDim.x][t_stride]
     size_t t_stride;
     unsigned int* job_counter;
+    uint64_t magic_W, magic_GW, magic_VW;  // FastDiv magics of W, 2W+1, W+1 (a 64-bit division per thread otherwise)
 };
 
 template <int DIM>

@@ -415,7 +415,7 @@ struct SmallCtx {
 template <int DIM>
 __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ unsigned int s_job;
+    __shared__ unsigned int s_job, s_next;
     __shared__ int s_count, s_K, s_ncross;
     __shared__ unsigned long long s_argmax;
     __shared__ unsigned int s_lo, s_hi;
@@ -439,9 +439,11 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         if (S.prof && tid == 0) { long long t1 = clock64(); atomicAdd(S.prof + (slot), (unsigned long long)(t1 - t0)); t0 = t1; } \
     } while (0)
 
+    if (tid == 0) s_next = atomicAdd(A.job_counter, 1u);
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_job = atomicAdd(A.job_counter, 1u); s_count = 0; s_ncross = 0; s_argmax = 0ull; s_lo = 0xFFFFFFFFu; s_hi = 0u; }
+        // one job is always claimed ahead: its map is prefetched into L2 while this one is being emitted
+        if (tid == 0) { s_job = s_next; s_next = atomicAdd(A.job_counter, 1u); s_count = 0; s_ncross = 0; s_argmax = 0ull; s_lo = 0xFFFFFFFFu; s_hi = 0u; }
         __syncthreads();
         const unsigned int job = s_job;
         if (job >= n_jobs) break;
@@ -593,7 +595,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             const float* __restrict__ f = g.f;
             for (int c0 = 0; c0 < W; c0 += cols_per_band) {
             const int c1 = min(W, c0 + cols_per_band), bw = c1 - c0, nb = H * bw;  // this band: columns c0 .. c1-1
-            const FastDiv divW((uint32_t)bw);
+            const FastDiv divW = bw == W ? FastDiv(A.magic_W, (uint32_t)W) : FastDiv((uint32_t)bw);
             const int chunk = ((nb + 32 * 128 - 1) / (32 * 128)) * 128;  // nodes per warp
             const int wbeg = min(nb, warp * chunk), wend = min(nb, wbeg + chunk);
             const int trips = (wend - wbeg + 127) >> 7;                  // <= 16
@@ -1149,7 +1151,14 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
 
         // ---- emit: every thread owns a contiguous run of basins, so ONE block scan yields
         //      deterministic slots in basin (= raster) order
-        const FastDiv divRW((uint32_t)GW), divVW((uint32_t)VW);  // exact for ids < 2^22 (multiply-shift)
+        const FastDiv divRW(A.magic_GW, (uint32_t)GW), divVW(A.magic_VW, (uint32_t)VW);  // exact for ids < 2^24 (multiply-shift)
+        {   // the next job's map: one 128-byte line per prefetch, into L2 only (it is read once)
+            const unsigned int nj = s_next;
+            if (nj < n_jobs) {
+                const char* nm = reinterpret_cast<const char*>(A.maps[nj / (unsigned)A.n_maps] + (size_t)(nj % (unsigned)A.n_maps) * N);
+                for (int i = tid; i < (N * 4 + 127) / 128; i += nt) asm volatile("prefetch.global.L2 [%0];" :: "l"(nm + (size_t)i * 128));
+            }
+        }
         PairRec* out = A.pairs[set] + (size_t)map * A.cap;
         uint64_t* skeys = A.skeys[set] ? A.skeys[set] + (size_t)map * A.cap : nullptr;
         {

@@ -44,6 +44,8 @@ struct FastDiv {
     uint64_t magic;
     uint32_t d;
     __host__ __device__ explicit FastDiv(uint32_t d_) : magic(((1ull << 40) + d_ - 1) / d_), d(d_) {}
+    __host__ __device__ FastDiv(uint64_t magic_, uint32_t d_) : magic(magic_), d(d_) {}  // magic computed by the host
+    __host__ __device__ static uint64_t magic_of(uint32_t d_) { return ((1ull << 40) + d_ - 1) / d_; }
     __device__ __forceinline__ uint32_t div(uint32_t n) const { return (uint32_t)(((uint64_t)n * magic) >> 40); }
 };
 

@@ -152,6 +152,8 @@ int launch_ph(const float* m0, const float* m1, int n_sets, const Layout& L, int
         a.counts[s] = at<int32_t>(ws, L.counts[s]);
     }
     a.n_sets = n_sets; a.n_maps = L.M; a.H = H; a.W = W; a.cap = L.cap;
+    a.magic_W = tl::FastDiv::magic_of((uint32_t)W); a.magic_GW = tl::FastDiv::magic_of((uint32_t)(2 * W + 1));
+    a.magic_VW = tl::FastDiv::magic_of((uint32_t)(W + 1));
     a.T = at<uint64_t>(ws, L.T); a.t_stride = L.t_stride;
     a.job_counter = at<unsigned int>(ws, L.counter);
     TL_CUDA(cudaMemsetAsync(a.job_counter, 0, 256, st));
