@@ -63,6 +63,9 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0:  # nvidia-smi takes a few 100 ms to start streaming:
+                time.sleep(0.01)                            # the timed region (tens of ms) must not be over by then
         except Exception:
             self.proc = None
 
@@ -74,6 +77,10 @@ class ClockSampler:
         """Start of the timed region: samples before this point are dropped (if any remain after)."""
         self.first = len(self.rows)
 
+    def mark_end(self):
+        """End of the device-timed region (the sampler keeps running through the end-to-end region)."""
+        self.last = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -82,14 +89,22 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        if len(self.rows) > getattr(self, "first", 0):
-            self.rows = self.rows[getattr(self, "first", 0):]
+        first, last = getattr(self, "first", 0), getattr(self, "last", None)
+        window = "timed region"
+        if last is not None and last > first:
+            self.rows = self.rows[first:last]
+        elif len(self.rows) > first:  # the device-timed region was shorter than one sampling period
+            self.rows = self.rows[first:]
+            window = "timed + end-to-end region"
+        else:
+            window = "before the timed region"
+        self.window = window
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": self.window}
 
 
 def cpu_arm(pred, truth, nthreads, steps, warmup):
@@ -234,11 +249,13 @@ def main():
     calls = (ctypes.c_int * 2)()
     L.tl_timing_read(sums, calls)
     L.tl_timing_enable(0)
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        sampler.mark_end()
 
     for _ in range(3):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:
