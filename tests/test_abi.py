@@ -65,3 +65,30 @@ def test_product_has_no_cpu_path_and_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "topo_oracle" not in text, f
+
+
+def test_fused_call_site_functions_have_no_cpu_path_either():
+    """topo_loss_from_logits / resample / postprocess_masks (rows F1, F3): same rules as topo_loss --
+    CUDA float32 only, the reference's early-out, argument errors raised on the host."""
+    import torch
+    import dilabhelmholtzoct_b200 as tlb
+    x = torch.randn(2, 3, 8, 8)
+    assert tlb.topo_loss_from_logits(x, x, 0.0, feat_d=1, interp=4) == 0.0
+    with pytest.raises(ValueError, match="CUDA"):
+        tlb.topo_loss_from_logits(x, x, 0.1, feat_d=1, interp=4)
+    with pytest.raises(ValueError):
+        tlb.topo_loss_from_logits(x, x[:, :2], 0.1, feat_d=1)
+    with pytest.raises(ValueError, match="CUDA"):
+        tlb.resample(x, 4)
+    with pytest.raises(ValueError, match="CUDA"):
+        tlb.postprocess_masks(x, (6, 8), (5, 7), padded_size=8)
+
+
+def test_resample_and_postprocess_argument_errors_from_the_library():
+    from dilabhelmholtzoct_b200 import _lib
+    L = _lib.lib()
+    assert L.tl_resample_forward(None, 1, 8, 8, 4, 1, None, None) == -1 and b"null" in L.tl_last_error()
+    assert L.tl_resample_forward(1, 0, 8, 8, 4, 1, 1, None) == -1
+    assert L.tl_postprocess_forward(1, 1, 8, 8, 32, 40, 32, 16, 16, 1, None) == -1   # crop larger than the intermediate
+    assert b"crop" in L.tl_last_error()
+    assert L.tl_postprocess_backward(None, 1, 8, 8, 32, 32, 32, 16, 16, None, None) == -1
