@@ -690,7 +690,9 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             const uint32_t par_s = (uint32_t)__cvta_generic_to_shared(par);
             for (int round = 0;; ++round) {
                 int pending = 0;
-                for (int t = 0; t < trips; ++t) {
+                // bottom rows first: most ties point DOWN (plateaus), so a row that jumps after the rows below it
+                // sees their already shortened pointers and a vertical run collapses within one round
+                for (int t = trips - 1; t >= 0; --t) {
                     const int x = wbeg + t * 128 + lane * 4;
                     const bool act = x < wend && ((donebits >> (4 * t)) & 15ull) != 15ull;
                     if (!__any_sync(0xFFFFFFFFu, act)) continue;
