@@ -61,6 +61,7 @@ struct MatchArgs {
     double* v; double* minv; double* u;
     int32_t* way; int32_t* pcol; uint8_t* used;
     size_t stride_c, stride_r;
+    unsigned int* counter;  // dynamic work counter (zeroed by the caller) or null: static round-robin over CTAs
 };
 
 __device__ __forceinline__ double block_sum(double x, double* s_red) {
@@ -90,7 +91,16 @@ __global__ void __launch_bounds__(kMatchThreads) match_kernel(MatchArgs A) {
     const float q = A.q;
     const double kInf = __longlong_as_double(0x7FF0000000000000LL);
 
-    for (int k = blockIdx.x; k < A.n_diag; k += gridDim.x) {
+    __shared__ int s_k;
+    // maps with a non-empty ground-truth diagram cost 10-100x the others: hand the maps out dynamically
+    for (int k = blockIdx.x;; k += gridDim.x) {
+        if (A.counter) {
+            __syncthreads();
+            if (tid == 0) s_k = (int)atomicAdd(A.counter, 1u);
+            __syncthreads();
+            k = s_k;
+        }
+        if (k >= A.n_diag) break;
         const int n = A.d1.rows(k), m = A.d2.rows(k);
         const char* r1 = A.d1.first(k);
         const char* r2 = A.d2.first(k);

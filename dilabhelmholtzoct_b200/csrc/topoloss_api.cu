@@ -315,6 +315,7 @@ int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W
     m.match1 = at<int32_t>(ws, L.match1);
     m.fill1 = at<tl::PairRec>(ws, L.pairs[0]);
     fill_match_scratch(m, ws, L.v, L.minv, L.u, L.way, L.pcol, L.used, L.stride_c, L.stride_r);
+    m.counter = at<unsigned int>(ws, L.counter) + 32;  // byte 128 of the counter block launch_ph zeroed
     tl::match_kernel<<<L.M < kMatchSlots ? L.M : kMatchSlots, tl::kMatchThreads, 0, st>>>(m);
     TL_CUDA(cudaGetLastError());
     TL_MARK(call, 3, st);
@@ -427,6 +428,7 @@ int tl_wasserstein(const float* D1, const int32_t* off1, const float* D2, const 
     m.d1 = tl::Diagrams{reinterpret_cast<const char*>(D1), 8, off1, nullptr, 0};
     m.d2 = tl::Diagrams{reinterpret_cast<const char*>(D2), 8, off2, nullptr, 0};
     m.n_diag = n_diag; m.q = q; m.loss_r = 0; m.cost = cost; m.tpers = nullptr; m.match1 = match1; m.fill1 = nullptr;
+    m.counter = nullptr;
     fill_match_scratch(m, ws, ov, ominv, ou, oway, opcol, oused, sc, sr);
     tl::match_kernel<<<slots, tl::kMatchThreads, 0, static_cast<cudaStream_t>(stream)>>>(m);
     TL_CUDA(cudaGetLastError());
