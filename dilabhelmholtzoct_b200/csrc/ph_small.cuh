@@ -16,6 +16,7 @@
 // position among its edges, value = its own), so it merges into OUTSIDE at zero persistence first.
 #pragma once
 #include "ph_kernel.cuh"
+#include "ph_binary.cuh"
 
 namespace tl {
 
@@ -354,6 +355,7 @@ __device__ __forceinline__ void merge_lanes(const TRef& T, const CrossEdge* __re
     }
 }
 
+
 struct PhSmallArgs {
     PhArgs base;
     CrossEdge* elist;    // [grid][e_stride] edges that cross two basins
@@ -363,6 +365,7 @@ struct PhSmallArgs {
     TEntry* T2g;         // [grid][k_stride] fallback triplet table
     size_t k_stride;
     unsigned long long* prof;  // optional [8] phase cycle counters
+    int binary_path;           // 1: try the two-valued fast path first (H1)
 };
 
 template <int DIM>
@@ -450,6 +453,14 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         if (S.prof && tid == 0) t0 = clock64();
         // all prediction maps first (heavy), ground-truth maps (light) fill the tail of the launch
         const int set = (int)(job / (unsigned)A.n_maps), map = (int)(job % (unsigned)A.n_maps);
+        // two-valued maps (one-hot ground truth): run-based labelling on a bit mask, no merge tree; a probe of
+        // the first words sends every other map on to the generic path
+        if (DIM == 1 && S.binary_path &&
+            binary_h1_pairs(A.maps[set] + (size_t)map * N, H, W, smem, kSmallSmemBytes, A.pairs[set] + (size_t)map * A.cap,
+                            A.skeys[set] ? A.skeys[set] + (size_t)map * A.cap : nullptr, A.cap, &A.counts[set][map], S.prof)) {
+            TL_PROF(0);
+            continue;
+        }
         SmallCtx<DIM> cx(A.maps[set] + (size_t)map * N, H, W, par);
         const Geo<DIM>& g = cx.g;
         const int NN = g.NN, GW = g.GW, VW = g.VW;

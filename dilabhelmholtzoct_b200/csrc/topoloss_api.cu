@@ -181,6 +181,8 @@ int launch_ph(const float* m0, const float* m1, int n_sets, const Layout& L, int
         sa.elist = at<tl::CrossEdge>(ws, L.elist); sa.e_stride = L.e_stride;
         const char* pe = getenv("TL_PROFILE");
         sa.prof = (pe && pe[0] == '1') ? at<unsigned long long>(ws, L.counter) + 8 : nullptr;
+        const char* nb = getenv("TL_NO_BINARY");
+        sa.binary_path = !(nb && nb[0] == '1');
         if (dim == 1) {
             TL_CUDA(cudaFuncSetAttribute(tl::ph_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl::kSmallSmemBytes));
             tl::ph_small_kernel<1><<<grid, tl::kPhThreads, tl::kSmallSmemBytes, st>>>(sa);

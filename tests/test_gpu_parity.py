@@ -348,3 +348,61 @@ def test_wasserstein_large_truth_diagrams():
     for k in range(len(D1)):
         want, _ = oracle.wasserstein(D1[k], D2[k], 2.0)
         assert abs(cost[k] - want) <= 1e-9 + 1e-7 * abs(want), (k, cost[k], want)
+
+
+def _blobs(rng, size, n_blobs, lo=0.0, hi=1.0):
+    yy, xx = np.mgrid[0:size, 0:size]
+    f = np.full((size, size), lo, np.float32)
+    for _ in range(n_blobs):
+        cy, cx = rng.integers(0, size, 2)
+        ry, rx = rng.integers(1, max(2, size // 6), 2)
+        f[((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0] = hi
+    for _ in range(n_blobs // 2):  # holes inside blobs, diagonal contacts
+        cy, cx = rng.integers(0, size, 2)
+        f[max(0, cy - 1):cy + 1, max(0, cx - 1):cx + 1] = lo
+    return f
+
+
+@pytest.mark.parametrize("size", [2, 7, 33, 64, 100, 256])
+def test_pairs_two_valued_maps(size):
+    """Two-valued maps take the bit-mask / run union-find path (csrc/ph_binary.cuh): random densities,
+    blobs with holes, either value at pixel 0, arbitrary (lo, hi) incl. negative values and -0.0."""
+    rng = np.random.default_rng(200 + size)
+    maps = []
+    for p in (0.05, 0.3, 0.5, 0.7, 0.95):
+        maps.append((rng.random((size, size)) < p).astype(np.float32))
+    maps.append(1.0 - maps[1])
+    maps.append(maps[2] * 3.5 - 1.25)
+    maps.append(np.where(maps[3] > 0, np.float32(-0.0), np.float32(-2.0)).astype(np.float32))
+    maps.append(_blobs(rng, size, 6))
+    maps.append(_blobs(rng, size, 12, lo=1.0, hi=0.0) if size > 2 else maps[0])
+    maps.append(np.zeros((size, size), np.float32))
+    stripes = np.zeros((size, size), np.float32); stripes[:, 1::2] = 1.0; stripes[0] = stripes[-1] = 0.0
+    maps.append(stripes)
+    maps = np.stack(maps).astype(np.float32)
+    _assert_same_pairs(maps, 1)
+    _assert_same_pairs(maps, 0)  # H0 has no two-valued short-cut: generic path on the same maps
+
+
+def test_pairs_two_valued_1024_and_run_overflow():
+    """1024x1024 masks (BASELINE configs[4] ground truth) and a 512x512 checkerboard whose 131 072 runs do
+    not fit the run table: the kernel must fall back to the generic path and still be exact."""
+    rng = np.random.default_rng(12)
+    _assert_same_pairs(np.stack([_blobs(rng, 1024, 40), (rng.random((1024, 1024)) < 0.55).astype(np.float32)]), 1)
+    yy, xx = np.mgrid[0:512, 0:512]
+    _assert_same_pairs(((yy + xx) % 2).astype(np.float32)[None], 1)
+    yy, xx = np.mgrid[0:256, 0:256]
+    _assert_same_pairs(((yy + xx) % 2).astype(np.float32)[None], 1)  # 32 768 runs: still on the bit-mask path
+
+
+def test_pairs_repeatable_at_c2_scale():
+    """Lock-free merge + reductions at the headline size: 3 runs over 56 noisy 256x256 maps, identical pairs."""
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, _ = make_batch(4, 256, 256, seed=77)
+    maps = pred.reshape(-1, 256, 256).numpy()
+    a = _gpu_pairs(maps, 1)
+    for _ in range(3):
+        b = _gpu_pairs(maps, 1)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    want = oracle.cubical_pairs(maps[5], 1)
+    assert np.array_equal(a[5], want)

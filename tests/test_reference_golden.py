@@ -1,0 +1,99 @@
+"""Parity against vectors produced by the REAL reference (torch_topological -> gudhi / POT) when
+``tests/golden/reference_vectors.json`` exists; it is written by ``tests/golden/make_golden_reference.py`` on a
+box that has those packages.  The build container does not, so here these tests are skipped and
+parity stays UNPINNED -- but the pin is one command away."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.json")
+needs_fixture = pytest.mark.skipif(not os.path.exists(FIXTURE), reason="reference deps absent (no reference_vectors.json)")
+REL = 1e-5
+
+
+def _doc():
+    with open(FIXTURE) as fh:
+        return json.load(fh)
+
+
+def _as_sets(pairs):
+    return sorted(map(tuple, pairs))
+
+
+@needs_fixture
+def test_oracle_pairs_equal_the_reference():
+    for case in _doc()["pairs"]:
+        f = np.array(case["image"], dtype=np.float32)
+        for dim in (0, 1):
+            got = oracle.cubical_pairs(f, dim).tolist()
+            want = case[f"h{dim}"]
+            # torch_topological lists regular pairs in gudhi's order and the essential H0 class last
+            assert got == want, (case["name"], dim)
+
+
+@needs_fixture
+def test_oracle_loss_and_gradient_equal_the_reference():
+    import torch
+    for case in _doc()["losses"]:
+        pred, truth = np.array(case["pred"], np.float32), np.array(case["truth"], np.float32)
+        if case["interp"]:
+            size = (case["interp"],) * 2
+            pred_t = torch.tensor(pred, requires_grad=True)
+            ps = torch.nn.functional.interpolate(pred_t, size=size, mode="bilinear", align_corners=True)
+            ts = torch.nn.functional.interpolate(torch.tensor(truth), size=size, mode="bilinear", align_corners=True)
+            loss, g, _ = oracle.topo_loss(ps.detach().numpy(), ts.numpy(), case["lamda"], feat_d=case["feat_d"], loss_q=case["q"])
+            ps.backward(torch.tensor(g))
+            grad = pred_t.grad.numpy()
+        else:
+            B = pred.shape[0]
+            if B == 1:  # the .squeeze() quirk: every channel is its own image
+                p2, t2 = pred.transpose(1, 0, 2, 3), truth.transpose(1, 0, 2, 3)
+                loss, g, _ = oracle.topo_loss(p2, t2, case["lamda"], feat_d=case["feat_d"], loss_q=case["q"])
+                grad = g.transpose(1, 0, 2, 3)
+            else:
+                loss, grad, _ = oracle.topo_loss(pred, truth, case["lamda"], feat_d=case["feat_d"], loss_q=case["q"])
+        want_g = np.array(case["grad"], np.float32)
+        assert abs(loss - case["loss"]) <= REL * abs(case["loss"]) + 1e-12
+        assert np.abs(grad - want_g).max() <= REL * np.abs(want_g).max() + 1e-12
+
+
+@needs_fixture
+@pytest.mark.gpu
+def test_cuda_path_equals_the_reference():
+    import torch
+    import dilabhelmholtzoct_b200 as tlb
+    doc = _doc()
+    for case in doc["pairs"]:
+        f = np.array(case["image"], dtype=np.float32)
+        if f.shape[0] != f.shape[1]:
+            continue
+        x = torch.tensor(f, device="cuda")[None]
+        for dim in (0, 1):
+            assert tlb.persistence_pairs(x, dim)[0].cpu().tolist() == case[f"h{dim}"], (case["name"], dim)
+    for case in doc["losses"]:
+        p = torch.tensor(case["pred"], device="cuda", requires_grad=True)
+        loss = tlb.topo_loss(p, torch.tensor(case["truth"], device="cuda"), case["lamda"], interp=case["interp"],
+                             feat_d=case["feat_d"], loss_q=case["q"])
+        loss.backward()
+        want_g = np.array(case["grad"], np.float32)
+        assert abs(float(loss) - case["loss"]) <= REL * abs(case["loss"]) + 1e-12
+        assert np.abs(p.grad.cpu().numpy() - want_g).max() <= REL * np.abs(want_g).max() + 1e-12
+
+
+def test_generator_reports_absent_dependencies_cleanly():
+    """In this container the generator must exit 2 without writing anything (and never crash)."""
+    import subprocess
+    import sys
+    try:
+        import torch_topological  # noqa: F401
+        pytest.skip("torch_topological is importable here: run the generator instead")
+    except ImportError:
+        pass
+    gen = os.path.join(os.path.dirname(FIXTURE), "make_golden_reference.py")
+    r = subprocess.run([sys.executable, gen, "/nonexistent"], capture_output=True, text=True)
+    assert r.returncode == 2 and "reference deps absent" in r.stderr
+    assert not os.path.exists(FIXTURE) or os.path.getsize(FIXTURE) > 0
