@@ -265,7 +265,7 @@ def main():
     value = gb / (ms_step * 1e-3)
     e2e_value = gb / (ms_e2e * 1e-3)
     peak, peak_src = _peaks()
-    stages = ["persistence", "segmented_sort", "matching", "loss", "grad_zero", "grad_scatter"]
+    stages = ["persistence", "unused_sort", "matching", "loss", "unused", "grad_fill_scatter"]
     nf, nb = max(1, calls[0]), max(1, calls[1])
     stage_ms = {s: (sums[i] / (nf if i < 4 else nb)) for i, s in enumerate(stages)}
     dom = max(stage_ms, key=stage_ms.get)
@@ -291,7 +291,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "masks/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(pred_h.numel() * 4 + truth_h.numel() * 4), "d2h_bytes_per_step": 4,
                 "api": f"topo_loss_from_host(pinned pred, pinned truth, chunks={E2E_CHUNKS}): H2D pipelined against the kernels"},
-        "gpu_launches": 4 * args.steps,  # persistence, matching, loss, grad scatter (+ 2 memsets) per step
+        "gpu_launches": 5 * args.steps,  # persistence, matching (2 kernels), loss, gradient fill + scatter (+ 1 memset) per step
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

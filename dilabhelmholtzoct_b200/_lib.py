@@ -11,15 +11,22 @@ _LIB = None
 
 c_fp = ctypes.c_void_p  # device pointers travel as integers
 TL_OK = 0
-ABI_VERSION = 1
+ABI_VERSION = 2
+OPT_FORCE_GLOBAL_KERNEL, OPT_PROFILE, OPT_NO_BINARY_PATH, OPT_WORST_CASE_WORKSPACE = 0, 1, 2, 3
+STATUS_BITS = {1: "pair arena exhausted (pass a larger state buffer: TL_ARENA_FACTOR / set_arena_factor)",
+               2: "basin tables exhausted (set TL_OPT_WORST_CASE_WORKSPACE)", 4: "a map holds a NaN"}
 
 SIGNATURES = {
     "tl_version": (ctypes.c_int, []),
     "tl_last_error": (ctypes.c_char_p, []),
     "tl_max_pairs": (ctypes.c_int, [ctypes.c_int] * 3),
-    "tl_workspace_bytes": (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_size_t)]),
+    "tl_set_option": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "tl_get_option": (ctypes.c_int, [ctypes.c_int]),
+    "tl_status": (ctypes.c_int, [c_fp, ctypes.POINTER(ctypes.c_int), c_fp]),
+    "tl_workspace_bytes": (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_size_t)] * 2),
+    "tl_pairs_workspace_bytes": (ctypes.c_int, [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_size_t)]),
     "tl_forward": (ctypes.c_int, [c_fp, c_fp] + [ctypes.c_int] * 5 + [ctypes.c_float, ctypes.c_float,
-                                  ctypes.c_int, ctypes.c_int, c_fp, ctypes.c_size_t, c_fp, c_fp]),
+                                  ctypes.c_int, ctypes.c_int, c_fp, ctypes.c_size_t, c_fp, ctypes.c_size_t, c_fp, c_fp]),
     "tl_backward": (ctypes.c_int, [c_fp, c_fp, ctypes.c_size_t] + [ctypes.c_int] * 5 +
                     [ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, c_fp, c_fp]),
     "tl_persistence_pairs": (ctypes.c_int, [c_fp] + [ctypes.c_int] * 4 + [c_fp, ctypes.c_size_t, c_fp,

@@ -18,31 +18,15 @@ namespace tl {
 
 constexpr int kMatchThreads = 1024;
 
-__device__ __forceinline__ float powq(float x, float q) { return q == 2.0f ? x * x : powf(x, q); }
-// torch.cdist(p=inf) entry, then .pow(q)
-__device__ __forceinline__ float cost_pp(float b, float d, float b2, float d2, float q) {
-    return powq(fmaxf(fabsf(b - b2), fabsf(d - d2)), q);
-}
-// torch.linalg.vector_norm(D - 0.5*(x+y), inf), then .pow(q)
-__device__ __forceinline__ float cost_diag(float b, float d, float q) {
-    const float h = 0.5f * (b + d);
-    return powq(fmaxf(fabsf(b - h), fabsf(d - h)), q);
-}
-
 struct Diagrams {          // strided view of (birth, death) rows
     const char* base;      // first row of diagram 0
     int stride;            // bytes between rows
-    const int32_t* off;    // row offsets [n_diag+1] or null
-    const int32_t* count;  // row counts [n_diag] (used when off == null; diagram k starts at k*cap)
-    int cap;
-    __device__ __forceinline__ int rows(int k) const {
-        if (off) return off[k + 1] - off[k];
-        int n = count[k];
-        return n > cap ? cap : n;
-    }
-    __device__ __forceinline__ const char* first(int k) const {
-        return base + (size_t)(off ? off[k] : k * cap) * stride;
-    }
+    const int32_t* off;     // row offsets [n_diag+1] (tl_wasserstein), or null
+    const uint32_t* start;  // first row of diagram k (pair arena; used with count when off == null)
+    const int32_t* count;   // row counts [n_diag]
+    __device__ __forceinline__ int rows(int k) const { return off ? off[k + 1] - off[k] : count[k]; }
+    __device__ __forceinline__ size_t first_row(int k) const { return off ? (size_t)off[k] : (size_t)start[k]; }
+    __device__ __forceinline__ const char* first(int k) const { return base + first_row(k) * stride; }
 };
 __device__ __forceinline__ float2 row_at(const char* first, int stride, int i) {
     return *reinterpret_cast<const float2*>(first + (size_t)i * stride);
@@ -55,26 +39,16 @@ struct MatchArgs {
     int loss_r;
     double* cost;        // [n_diag]
     double* tpers;       // [n_diag] or null
-    int32_t* match1;     // rows of d1 (same offsets as d1): matched row of d2 or -1
-    PairRec* fill1;      // when non-null: write the matched truth point into fill1[k*cap+i].tb/td
+    int32_t* match1;     // rows of d1 (same offsets as d1): matched row of d2 or -1; may be null
+    PairRec* fill1;      // when non-null: the records behind d1; matched truth points go to .tb / .td
+    const int32_t* list; // when non-null: the diagrams to process are list[0 .. *n_list)
+    const unsigned int* n_list;
     // per-CTA scratch
     double* v; double* minv; double* u;
     int32_t* way; int32_t* pcol; uint8_t* used;
     size_t stride_c, stride_r;
     unsigned int* counter;  // dynamic work counter (zeroed by the caller) or null: static round-robin over CTAs
 };
-
-__device__ __forceinline__ double block_sum(double x, double* s_red) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, o);
-    __syncthreads();
-    if (lane == 0) s_red[warp] = x;
-    __syncthreads();
-    double t = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
-    return t;
-}
 
 __global__ void __launch_bounds__(kMatchThreads) match_kernel(MatchArgs A) {
     __shared__ double s_red[kMatchThreads / 32];
@@ -93,6 +67,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_kernel(MatchArgs A) {
 
     __shared__ int s_k;
     // maps with a non-empty ground-truth diagram cost 10-100x the others: hand the maps out dynamically
+    const int n_work = A.list ? (int)*A.n_list : A.n_diag;
     for (int k = blockIdx.x;; k += gridDim.x) {
         if (A.counter) {
             __syncthreads();
@@ -100,7 +75,8 @@ __global__ void __launch_bounds__(kMatchThreads) match_kernel(MatchArgs A) {
             __syncthreads();
             k = s_k;
         }
-        if (k >= A.n_diag) break;
+        if (k >= n_work) break;
+        if (A.list) k = A.list[k];
         const int n = A.d1.rows(k), m = A.d2.rows(k);
         const char* r1 = A.d1.first(k);
         const char* r2 = A.d2.first(k);
@@ -109,13 +85,13 @@ __global__ void __launch_bounds__(kMatchThreads) match_kernel(MatchArgs A) {
         const int R = swp ? n : m, Cn = swp ? m : n;
         const char* rR = swp ? r1 : r2; const int stR = swp ? st1 : st2;
         const char* rC = swp ? r2 : r1; const int stC = swp ? st2 : st1;
-        int32_t* match1 = A.match1 + (A.d1.off ? A.d1.off[k] : k * A.d1.cap);
+        int32_t* match1 = A.match1 ? A.match1 + A.d1.first_row(k) : nullptr;
+        PairRec* recs1 = A.fill1 ? A.fill1 + A.d1.first_row(k) : nullptr;
 
         double part = 0.0, tp = 0.0;
 #pragma unroll 4
         for (int c = tid; c < Cn; c += nt) { float2 p = row_at(rC, stC, c); part += (double)cost_diag(p.x, p.y, q); }
-#pragma unroll 4
-        for (int i = tid; i < n; i += nt) match1[i] = -1;
+        if (match1) for (int i = tid; i < n; i += nt) match1[i] = -1;
         if (A.loss_r)
             for (int i = tid; i < n; i += nt) { float2 p = row_at(r1, st1, i); tp += pow(fabs((double)p.y - (double)p.x), (double)q); }
         double total = block_sum(part, s_red);
@@ -186,21 +162,173 @@ __global__ void __launch_bounds__(kMatchThreads) match_kernel(MatchArgs A) {
                 if (c <= Cn) {
                     const float2 pc = row_at(rC, stC, c - 1);
                     part2 += (double)cost_pp(pr.x, pr.y, pc.x, pc.y, q) - (double)cost_diag(pc.x, pc.y, q);
-                    if (swp) match1[r] = c - 1; else match1[c - 1] = r;
+                    const int i1 = swp ? r : c - 1;  // row of d1 / of d2 in this match
+                    if (match1) match1[i1] = swp ? c - 1 : r;
+                    if (recs1) { const float2 p2 = swp ? pc : pr; recs1[i1].tb = p2.x; recs1[i1].td = p2.y; }
                 } else part2 += (double)cost_diag(pr.x, pr.y, q);
             }
             total += block_sum(part2, s_red);
         }
         __syncthreads();
-        if (A.fill1) {
-            PairRec* recs = A.fill1 + (size_t)k * A.d1.cap;
-            for (int i = tid; i < n; i += nt) {
-                const int j = match1[i];
-                if (j >= 0) { const float2 p = row_at(r2, st2, j); recs[i].tb = p.x; recs[i].td = p.y; }
-            }
-        }
         if (tid == 0) { A.cost[k] = total; if (A.tpers) A.tpers[k] = A.loss_r ? tp : 0.0; }
         __syncthreads();
+    }
+}
+
+// ---- forward path of tl_forward: one pass over the maps.
+//
+// Segmentation ground truth has 0-5 pairs per map, so the assignment is almost always trivial:
+//   * min(n, m) == 0   every point goes to the diagonal; the cost is the two sums the persistence kernel
+//                      already formed while emitting (PairStore::dsum) -- no record is read at all;
+//   * min(n, m) <= 8   shortest augmenting paths with ALL state in shared memory.  The column potentials
+//                      are non-zero only for the <= R(R+1) columns that were ever on a search tree, and the
+//                      running column minima of a phase are recomputed from the <= R+1 tree rows instead of
+//                      stored, so nothing per column is kept: a step is one sweep over the columns plus one
+//                      block-wide arg-min.  Same algorithm, same tie-breaks (smallest column, earliest tree
+//                      row) as match_kernel and the oracle;
+//   * otherwise        the map is appended to a list that match_kernel (global scratch, a few slots)
+//                      works through afterwards.
+constexpr int kSmallR = 8;
+constexpr int kTouchMax = kSmallR * (kSmallR + 1) + 8;
+
+struct MatchFwdArgs {
+    PairStore ps;
+    int n_maps, loss_r;
+    float q;
+    double* cost;    // [n_maps]
+    double* tpers;   // [n_maps]
+    int32_t* heavy;  // [n_maps] maps left to match_kernel
+    unsigned int* n_heavy;
+    unsigned int* counter;
+};
+
+__global__ void __launch_bounds__(kMatchThreads) match_small_kernel(MatchFwdArgs A) {
+    __shared__ double s_red[kMatchThreads / 32];
+    __shared__ double s_bv[kMatchThreads / 32];
+    __shared__ int s_bk[kMatchThreads / 32], s_bw[kMatchThreads / 32];
+    __shared__ int s_k, s_done, s_nU, s_nT;
+    __shared__ float s_rb[kSmallR], s_rd[kSmallR];
+    __shared__ double s_rdiag[kSmallR], s_u[kSmallR + 1], s_tv[kTouchMax];
+    __shared__ int s_Ucol[kSmallR + 2], s_Urow[kSmallR + 2], s_tc[kTouchMax], s_tp[kTouchMax], s_tway[kTouchMax];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const float q = A.q;
+    const double kInf = __longlong_as_double(0x7FF0000000000000LL);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_k = (int)atomicAdd(A.counter, 1u);
+        __syncthreads();
+        const int k = s_k;
+        if (k >= A.n_maps) break;
+        const int n = A.ps.counts[0][k], m = A.ps.counts[1][k];
+        PairRec* rec1 = A.ps.arena + A.ps.offs[0][k];
+        const PairRec* rec2 = A.ps.arena + A.ps.offs[1][k];
+        double tp = 0.0;
+        if (A.loss_r) {  // total persistence of the prediction diagram (topological_loss.py:88-94)
+            for (int i = tid; i < n; i += nt) tp += pow(fabs((double)rec1[i].d - (double)rec1[i].b), (double)q);
+            tp = block_sum(tp, s_red);
+        }
+        const bool swp = n < m;
+        const int R = swp ? n : m, Cn = swp ? m : n;
+        if (R == 0 || R > kSmallR) {
+            if (tid == 0) {
+                A.tpers[k] = tp;
+                if (R == 0) A.cost[k] = A.ps.dsum[0][k] + A.ps.dsum[1][k];
+                else A.heavy[atomicAdd(A.n_heavy, 1u)] = k;
+            }
+            continue;
+        }
+        const PairRec* rR = swp ? rec1 : rec2;
+        const PairRec* rC = swp ? rec2 : rec1;
+        const int NC = Cn + R;
+        if (tid < R) {
+            const float b = rR[tid].b, d = rR[tid].d;
+            s_rb[tid] = b; s_rd[tid] = d; s_rdiag[tid] = (double)cost_diag(b, d, q);
+        }
+        if (tid <= R) s_u[tid] = 0.0;
+        if (tid == 0) s_nT = 0;
+        __syncthreads();
+        for (int r = 1; r <= R; ++r) {
+            if (tid == 0) { s_nU = 1; s_Ucol[0] = 0; s_Urow[0] = r; }
+            __syncthreads();
+            for (;;) {
+                const int nU = s_nU, nT = s_nT;
+                double best = kInf; int bestk = 0x7FFFFFFF, bestw = 0;
+                for (int c = 1 + tid; c <= NC; c += nt) {
+                    bool used = false;
+                    for (int t = 1; t < nU; ++t) used |= s_Ucol[t] == c;
+                    if (used) continue;
+                    double vc = 0.0;
+                    for (int t = 0; t < nT; ++t) if (s_tc[t] == c) vc = s_tv[t];
+                    float cb = 0.f, cd = 0.f; double cdg = 0.0;
+                    const bool real = c <= Cn;
+                    if (real) { cb = rC[c - 1].b; cd = rC[c - 1].d; cdg = (double)cost_diag(cb, cd, q); }
+                    double mv = kInf; int way = 0;
+                    for (int t = 0; t < nU; ++t) {  // tree rows in the order they joined: the first strict minimum wins
+                        const int i = s_Urow[t] - 1;
+                        const double cc = real ? (double)cost_pp(s_rb[i], s_rd[i], cb, cd, q) - cdg : s_rdiag[i];
+                        const double cur = cc - s_u[i + 1] - vc;
+                        if (cur < mv) { mv = cur; way = s_Ucol[t]; }
+                    }
+                    if (mv < best) { best = mv; bestk = c; bestw = way; }  // c ascending per thread: first minimum kept
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_down_sync(0xFFFFFFFFu, best, o);
+                    const int ok = __shfl_down_sync(0xFFFFFFFFu, bestk, o), ow = __shfl_down_sync(0xFFFFFFFFu, bestw, o);
+                    if (ob < best || (ob == best && ok < bestk)) { best = ob; bestk = ok; bestw = ow; }
+                }
+                if (lane == 0) { s_bv[warp] = best; s_bk[warp] = bestk; s_bw[warp] = bestw; }
+                __syncthreads();
+                if (tid == 0) {
+                    best = s_bv[0]; bestk = s_bk[0]; bestw = s_bw[0];
+                    for (int w = 1; w < nt / 32; ++w)
+                        if (s_bv[w] < best || (s_bv[w] == best && s_bk[w] < bestk)) { best = s_bv[w]; bestk = s_bk[w]; bestw = s_bw[w]; }
+                    const double delta = best; const int j1 = bestk;
+                    for (int t = 0; t < nU; ++t) s_u[s_Urow[t]] += delta;
+                    for (int t = 1; t < nU; ++t) {
+                        const int c = s_Ucol[t];
+                        for (int x = 0; x < nT; ++x) if (s_tc[x] == c) s_tv[x] -= delta;
+                    }
+                    int tj = -1;
+                    for (int x = 0; x < nT; ++x) if (s_tc[x] == j1) tj = x;
+                    if (tj < 0) { tj = nT; s_tc[tj] = j1; s_tv[tj] = 0.0; s_tp[tj] = 0; s_nT = nT + 1; }
+                    s_tway[tj] = bestw;
+                    if (s_tp[tj] == 0) {  // free column: flip the path back to the phase's row
+                        int j = j1;
+                        while (j != 0) {
+                            int xj = 0; for (int x = 0; x < s_nT; ++x) if (s_tc[x] == j) xj = x;
+                            const int jp = s_tway[xj];
+                            int pr = r;
+                            if (jp != 0) for (int x = 0; x < s_nT; ++x) if (s_tc[x] == jp) pr = s_tp[x];
+                            s_tp[xj] = pr;
+                            j = jp;
+                        }
+                        s_done = 1;
+                    } else {
+                        s_Ucol[nU] = j1; s_Urow[nU] = s_tp[tj]; s_nU = nU + 1;
+                        s_done = 0;
+                    }
+                }
+                __syncthreads();
+                if (s_done) break;
+            }
+        }
+        // cost of the optimum: every column goes to the diagonal (dsum) unless a row took it
+        if (tid == 0) {
+            double total = A.ps.dsum[swp ? 1 : 0][k];
+            for (int x = 0; x < s_nT; ++x) {
+                const int row = s_tp[x] - 1, c = s_tc[x];
+                if (row < 0) continue;
+                if (c <= Cn) {
+                    const float cb = rC[c - 1].b, cd = rC[c - 1].d;
+                    total += (double)cost_pp(s_rb[row], s_rd[row], cb, cd, q) - (double)cost_diag(cb, cd, q);
+                    const int i1 = swp ? row : c - 1;  // record of the prediction in this match
+                    rec1[i1].tb = swp ? cb : s_rb[row]; rec1[i1].td = swp ? cd : s_rd[row];
+                } else total += s_rdiag[row];
+            }
+            A.cost[k] = total;
+            A.tpers[k] = tp;
+        }
     }
 }
 
@@ -210,6 +338,7 @@ struct LossArgs {
     float q, lamda;
     float* loss_out;
     double* coef;  // [B] d loss / d S_b (NaN when S_b == 0, as autograd's 0 * inf)
+    const unsigned int* status;  // device status word: any bit set poisons the loss with NaN
 };
 
 __global__ void __launch_bounds__(256) loss_kernel(LossArgs A) {
@@ -231,25 +360,35 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs A) {
     if (tid == 0) {
         double loss = acc / Bg;
         if (A.loss_r) loss += reg / ((double)Bg * A.C);
-        *A.loss_out = (float)((double)A.lamda * loss);
+        // an exhausted arena / basin table or a NaN pixel makes the pairing incomplete: fail loudly
+        *A.loss_out = (A.status && *A.status) ? __int_as_float(0x7FC00000) : (float)((double)A.lamda * loss);
     }
 }
 
 struct GradArgs {
-    const PairRec* pairs; const int32_t* counts; const double* coef; const float* grad_loss;
-    int M, C, cap, N, B_global, loss_r;
+    const PairRec* arena; const uint32_t* offs; const int32_t* counts; const double* coef; const float* grad_loss;
+    int M, C, N, B_global, loss_r;
     float q, lamda;
     float* grad_pred;
 };
 
-__global__ void __launch_bounds__(256) grad_kernel(GradArgs A) {
+// One CTA per map: zero-fill the map's gradient (128-bit stores, the lines stay in L2), then scatter-add
+// the pairs into the critical pixels.  Fusing the fill keeps the atomics off cold DRAM lines and saves the
+// separate memset pass.
+__global__ void __launch_bounds__(512) grad_kernel(GradArgs A) {
     const double gl = A.grad_loss ? (double)__ldg(A.grad_loss) : 1.0;
     const double q = (double)A.q;
     for (int map = blockIdx.x; map < A.M; map += gridDim.x) {
-        int n = A.counts[map];
-        if (n > A.cap) n = A.cap;
-        const PairRec* recs = A.pairs + (size_t)map * A.cap;
+        const int n = A.counts[map];
+        const PairRec* recs = A.arena + A.offs[map];
         float* g = A.grad_pred + (size_t)map * A.N;
+        if (((reinterpret_cast<uintptr_t>(g) & 15) == 0) && (A.N & 3) == 0) {
+            float4* g4 = reinterpret_cast<float4*>(g);
+            for (int i = threadIdx.x; i < (A.N >> 2); i += blockDim.x) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (int i = threadIdx.x; i < A.N; i += blockDim.x) g[i] = 0.f;
+        }
+        __syncthreads();  // the fill is visible to the whole CTA before its atomics land on the same lines
         const double coef = A.coef[map / A.C] * gl;
         const double creg = (double)A.lamda / ((double)A.B_global * A.C) * gl;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -258,7 +397,7 @@ __global__ void __launch_bounds__(256) grad_kernel(GradArgs A) {
             if (isnan(r.tb)) {  // matched to the diagonal
                 const float h = 0.5f * (r.b + r.d);
                 const float x = fmaxf(fabsf(r.b - h), fabsf(r.d - h));
-                const double gg = x > 0.f ? q * pow((double)x, q - 1.0) : (q == 1.0 ? 1.0 : 0.0);
+                const double gg = x > 0.f ? (q == 2.0 ? 2.0 * (double)x : q * pow((double)x, q - 1.0)) : (q == 1.0 ? 1.0 : 0.0);
                 const double s = r.d > r.b ? 1.0 : (r.d < r.b ? -1.0 : 0.0);
                 gb = -0.5 * gg * s; gd = 0.5 * gg * s;
             } else {
@@ -277,6 +416,7 @@ __global__ void __launch_bounds__(256) grad_kernel(GradArgs A) {
             atomicAdd(g + r.cre, (float)gb);
             atomicAdd(g + r.des, (float)gd);
         }
+        __syncthreads();
     }
 }
 

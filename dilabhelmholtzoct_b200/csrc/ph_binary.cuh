@@ -48,11 +48,12 @@ __device__ __forceinline__ uint32_t bin_find(volatile uint16_t* par, uint32_t x)
 // All threads of the CTA call this (block-uniform).  Returns 1 when the map was handled (pairs and
 // count written), 0 when the caller must run the generic path (nothing has been written then).
 __device__ __noinline__ int binary_h1_pairs(const float* __restrict__ f, int H, int W, unsigned char* smem, int smem_bytes,
-                               PairRec* out, uint64_t* skeys, int cap, int32_t* count_out,
-                                            unsigned long long* prof) {
+                                            const PairStore& ps, int set, int map, unsigned long long* prof) {
     __shared__ unsigned int sb_omin, sb_omax;
     __shared__ int sb_wsum[32];
-    __shared__ int sb_total;
+    __shared__ int sb_total, sb_avail;
+    __shared__ unsigned long long sb_base;
+    __shared__ double sb_red[32];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     const int nw = (W + 31) >> 5, n_words = H * nw;
     // layout: mask u32[n_words] | pre u16[n_words] | par u16[R_cap] | border u8[R_cap]
@@ -98,6 +99,7 @@ __device__ __noinline__ int binary_h1_pairs(const float* __restrict__ f, int H, 
                     const int wi = (warp + (it + u) * nwarp) * 4;
                     const bool ok = it + u < it1 && wi < n_words;  // warp-uniform
                     const uint32_t v0 = mono32(raw[u].x), v1 = mono32(raw[u].y), v2 = mono32(raw[u].z), v3 = mono32(raw[u].w);
+                    if (ok && ((raw[u].x != raw[u].x) | (raw[u].y != raw[u].y) | (raw[u].z != raw[u].z) | (raw[u].w != raw[u].w))) { omin = 0u; omax = 0xFFFFFFFFu; }  // NaN: leave it to the generic path
                     unsigned nib = 0u;
                     if (ok) {
                         if (v0 != ref) { nib |= 1u; omin = min(omin, v0); omax = max(omax, v0); }
@@ -130,6 +132,7 @@ __device__ __noinline__ int binary_h1_pairs(const float* __restrict__ f, int H, 
                 const uint32_t v = mono32(raw[u]);
                 const bool other = okw && 32 * k + lane < W && v != ref;
                 if (other) { omin = min(omin, v); omax = max(omax, v); }
+                if (okw && 32 * k + lane < W && raw[u] != raw[u]) { omin = 0u; omax = 0xFFFFFFFFu; }  // NaN: leave it to the generic path
                 const unsigned bal = __ballot_sync(0xFFFFFFFFu, other);
                 if (lane == 0 && okw) m[wi] = bal;
             }
@@ -153,7 +156,7 @@ __device__ __noinline__ int binary_h1_pairs(const float* __restrict__ f, int H, 
     TLB_PROF(1);  // mask scan
     const uint32_t other = sb_omin;
     if (other > sb_omax) {  // no other value: constant map, no finite H1 pair
-        if (tid == 0) *count_out = 0;
+        if (tid == 0) { int av; ps_reserve(ps, set, map, 0, &av); ps.dsum[set][map] = 0.0; }
         return 1;
     }
     if (other < ref) {  // pixel 0 carries hi: flip the mask (bits past column W stay clear)
@@ -261,6 +264,12 @@ __device__ __noinline__ int binary_h1_pairs(const float* __restrict__ f, int H, 
             while (e) { e &= e - 1; if (par[x] == (uint16_t)x && !border[x]) ++mine; ++x; }
         }
         int slot = block_excl_scan(mine, total);
+        if (tid == 0) { int av; sb_base = ps_reserve(ps, set, map, total, &av); sb_avail = av; }
+        __syncthreads();
+        PairRec* out = ps.arena + sb_base;
+        uint64_t* skeys = ps.skeys ? ps.skeys + sb_base : nullptr;
+        const int avail = sb_avail;
+        double dacc = 0.0;
         if (mine) {
             for (int wi = w_beg; wi < w_end; ++wi) {
                 const int r = (int)divNW.div((uint32_t)wi), k = wi - r * nw;
@@ -270,7 +279,7 @@ __device__ __noinline__ int binary_h1_pairs(const float* __restrict__ f, int H, 
                     const int bit = __ffs(e) - 1;
                     e &= e - 1;
                     if (par[x] == (uint16_t)x && !border[x]) {
-                        if (slot < cap) {
+                        if (slot < avail) {
                             PairRec rec;
                             rec.des = r * W + 32 * k + bit;
                             rec.cre = rec.des + W;  // a blob off the border never reaches the last row
@@ -278,6 +287,7 @@ __device__ __noinline__ int binary_h1_pairs(const float* __restrict__ f, int H, 
                             rec.tb = rec.td = __int_as_float(0x7FC00000);
                             out[slot] = rec;
                             if (skeys) skeys[slot] = ((uint64_t)mono32(rec.d) << 32) | (uint32_t)rec.des;
+                            dacc += (double)cost_diag(rec.b, rec.d, ps.q);
                         }
                         ++slot;
                     }
@@ -285,8 +295,9 @@ __device__ __noinline__ int binary_h1_pairs(const float* __restrict__ f, int H, 
                 }
             }
         }
+        dacc = block_sum(dacc, sb_red);
+        if (tid == 0) ps.dsum[set][map] = dacc;
     }
-    if (tid == 0) *count_out = total;
     TLB_PROF(5);  // emit
 #undef TLB_PROF
     return 1;

@@ -45,10 +45,9 @@ constexpr int kPhThreads = 1024;
 
 struct PhArgs {
     const float* maps[2];   // set 0 (pred) / set 1 (truth); maps[1] may be null when n_sets == 1
-    PairRec* pairs[2];      // [n_maps][cap]
-    uint64_t* skeys[2];     // [n_maps][cap] sort key of each emitted pair (death-cell order), may be null
-    int32_t* counts[2];     // [n_maps]
-    int n_sets, n_maps, H, W, cap;
+    PairStore ps;           // record arena, per-map offsets / counts / diagonal-cost sums, status word
+    int n_sets, n_maps, H, W;
+    int cap;                // most pairs one map can have (per-CTA scratch strides)
     uint64_t* T;            // [gridDim.x][t_stride]
     size_t t_stride;
     unsigned int* job_counter;
@@ -136,9 +135,10 @@ struct Ph {
 template <int DIM>
 __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
     __shared__ unsigned int s_job;
-    __shared__ int s_count;
-    __shared__ unsigned long long s_argmax;
+    __shared__ int s_count, s_avail;
+    __shared__ unsigned long long s_argmax, s_base;
     __shared__ int s_wcnt[kPhThreads / 32];
+    __shared__ double s_red[kPhThreads / 32];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int H = A.H, W = A.W, N = H * W;
     uint64_t* T = A.T + (size_t)blockIdx.x * A.t_stride;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_job = atomicAdd(A.job_counter, 1u); s_count = 0; s_argmax = 0ull; }
+        if (tid == 0) { s_job = atomicAdd(A.job_counter, 1u); s_count = 0; s_avail = 0; s_argmax = 0ull; }
         __syncthreads();
         const unsigned int job = s_job;
         if (job >= n_jobs) break;
@@ -158,15 +158,23 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
 
         // ---- phase 0: every node is its own root
         for (int x = tid; x < NN; x += nt) T[x] = ((uint64_t)kCodeRoot << 32) | (uint32_t)x;
-        if (DIM == 0) {  // argmax(f), first in raster order: torch_topological's fake destroyer
+        {   // argmax(f), first in raster order: torch_topological's fake destroyer (H0); NaN check (the order is undefined)
             unsigned long long best = 0ull;
+            bool has_nan = false;
             for (int p = tid; p < N; p += nt) {
-                unsigned long long k = ((unsigned long long)mono32(__ldg(g.f + p)) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)p);
+                const float fv = __ldg(g.f + p);
+                has_nan |= fv != fv;
+                unsigned long long k = ((unsigned long long)mono32(fv) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)p);
                 best = k > best ? k : best;
             }
-            atomicMax(&s_argmax, best);
+            if (DIM == 0) atomicMax(&s_argmax, best);
+            if (has_nan) s_avail = -1;
         }
         __syncthreads();
+        if (s_avail < 0) {  // block-uniform
+            if (tid == 0) { int av; atomicOr(A.ps.status, kStNonFinite); ps_reserve(A.ps, set, map, 0, &av); A.ps.dsum[set][map] = 0.0; }
+            continue;
+        }
 
         // ---- phase 1: level-0 contraction along each node's earliest incident edge
         const int n_real = DIM == 1 ? N : NN;
@@ -284,33 +292,47 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
         }
         __syncthreads();
 
-        // ---- phase 3: emit pairs of positive persistence
-        PairRec* out = A.pairs[set] + (size_t)map * A.cap;
-        uint64_t* skeys = A.skeys[set] ? A.skeys[set] + (size_t)map * A.cap : nullptr;
+        // ---- phase 3: emit pairs of positive persistence.  Two passes over the nodes: count, reserve the
+        //      map's records in the arena, then write them in node (= raster) order.
+        auto emits = [&](int x, PairRec& rec, uint64_t& sk) {
+            const uint64_t t = ld_cg_u64(T + x);
+            const uint32_t code = (uint32_t)(t >> 32);
+            if (code != kCodeL0 && code != kCodeRoot) {
+                const uint32_t pos = code - 1;
+                const uint64_t ek = g.ekey(pos), nk = g.nkey(x);
+                if ((uint32_t)(ek >> 32) != (uint32_t)(nk >> 32)) {
+                    if (DIM == 1) { rec.cre = g.edge_top(pos); rec.des = x; sk = ~nk; }  // death cell = square x
+                    else { g.vertex_val(x / VW, x % VW, &rec.cre); rec.des = g.edge_top(pos); sk = ek; }  // death cell = edge
+                    return true;
+                }
+            } else if (DIM == 0 && code == kCodeRoot) {  // the essential class, emitted last
+                g.vertex_val(x / VW, x % VW, &rec.cre);
+                rec.des = (int)(0xFFFFFFFFu - (uint32_t)s_argmax);
+                sk = ~0ull;
+                return true;
+            }
+            return false;
+        };
+        {
+            int mine = 0;
+            for (int x = tid; x < NN; x += nt) { PairRec r; uint64_t k; mine += emits(x, r, k) ? 1 : 0; }
+            mine = __reduce_add_sync(0xFFFFFFFFu, mine);
+            if ((tid & 31) == 0 && mine) atomicAdd(&s_count, mine);
+        }
+        __syncthreads();
+        if (tid == 0) { int avail; s_base = ps_reserve(A.ps, set, map, s_count, &avail); s_avail = avail; }
+        __syncthreads();
+        PairRec* out = A.ps.arena + s_base;
+        uint64_t* skeys = A.ps.skeys ? A.ps.skeys + s_base : nullptr;
+        const int avail = s_avail;
+        double dacc = 0.0;
         int emit_base = 0;
         for (int x0 = 0; x0 < NN; x0 += nt) {
             const int x = x0 + tid;
             bool emit = false;
             PairRec rec;
             uint64_t sk = 0;
-            if (x < NN) {
-                const uint64_t t = ld_cg_u64(T + x);
-                const uint32_t code = (uint32_t)(t >> 32);
-                if (code != kCodeL0 && code != kCodeRoot) {
-                    const uint32_t pos = code - 1;
-                    const uint64_t ek = g.ekey(pos), nk = g.nkey(x);
-                    if ((uint32_t)(ek >> 32) != (uint32_t)(nk >> 32)) {
-                        emit = true;
-                        if (DIM == 1) { rec.cre = g.edge_top(pos); rec.des = x; sk = ~nk; }  // death cell = square x
-                        else { g.vertex_val(x / VW, x % VW, &rec.cre); rec.des = g.edge_top(pos); sk = ek; }  // death cell = edge
-                    }
-                } else if (DIM == 0 && code == kCodeRoot) {  // the essential class, emitted last
-                    emit = true;
-                    g.vertex_val(x / VW, x % VW, &rec.cre);
-                    rec.des = (int)(0xFFFFFFFFu - (uint32_t)s_argmax);
-                    sk = ~0ull;
-                }
-            }
+            if (x < NN) emit = emits(x, rec, sk);
             // deterministic slots: block-wide scan in node (= raster) order, no atomics
             const unsigned ballot = __ballot_sync(0xFFFFFFFFu, emit);
             if ((tid & 31) == 0) s_wcnt[tid >> 5] = __popc(ballot);
@@ -319,20 +341,20 @@ __global__ void __launch_bounds__(kPhThreads) ph_kernel(PhArgs A) {
             for (int w = 0; w < kPhThreads / 32; ++w) { const int v = s_wcnt[w]; total += v; if (w < (tid >> 5)) before += v; }
             if (emit) {
                 const int slot = emit_base + before + __popc(ballot & lanemask_lt());
-                if (slot < A.cap) {
+                if (slot < avail) {
                     rec.b = __ldg(g.f + rec.cre);
                     rec.d = __ldg(g.f + rec.des);
                     rec.tb = rec.td = __int_as_float(0x7FC00000);
                     out[slot] = rec;
                     if (skeys) skeys[slot] = sk;
+                    dacc += (double)cost_diag(rec.b, rec.d, A.ps.q);
                 }
             }
             emit_base += total;
             __syncthreads();
         }
-        if (tid == 0) s_count = emit_base;
-        __syncthreads();
-        if (tid == 0) A.counts[set][map] = s_count;
+        dacc = block_sum(dacc, s_red);
+        if (tid == 0) A.ps.dsum[set][map] = dacc;
     }
 }
 

@@ -419,10 +419,12 @@ template <int DIM>
 __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned int s_job, s_next;
-    __shared__ int s_count, s_K, s_ncross;
+    __shared__ int s_count, s_K, s_ncross, s_nan;
     __shared__ unsigned long long s_argmax;
     __shared__ unsigned int s_lo, s_hi;
     __shared__ int s_wcnt[kPhThreads / 32];
+    __shared__ double s_red[kPhThreads / 32];
+    __shared__ unsigned long long s_base;
     const PhArgs& A = S.base;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int H = A.H, W = A.W, N = H * W;
@@ -446,7 +448,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
     for (;;) {
         __syncthreads();
         // one job is always claimed ahead: its map is prefetched into L2 while this one is being emitted
-        if (tid == 0) { s_job = s_next; s_next = atomicAdd(A.job_counter, 1u); s_count = 0; s_ncross = 0; s_argmax = 0ull; s_lo = 0xFFFFFFFFu; s_hi = 0u; }
+        if (tid == 0) { s_job = s_next; s_next = atomicAdd(A.job_counter, 1u); s_count = 0; s_ncross = 0; s_nan = 0; s_argmax = 0ull; s_lo = 0xFFFFFFFFu; s_hi = 0u; }
         __syncthreads();
         const unsigned int job = s_job;
         if (job >= n_jobs) break;
@@ -456,8 +458,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         // two-valued maps (one-hot ground truth): run-based labelling on a bit mask, no merge tree; a probe of
         // the first words sends every other map on to the generic path
         if (DIM == 1 && S.binary_path &&
-            binary_h1_pairs(A.maps[set] + (size_t)map * N, H, W, smem, kSmallSmemBytes, A.pairs[set] + (size_t)map * A.cap,
-                            A.skeys[set] ? A.skeys[set] + (size_t)map * A.cap : nullptr, A.cap, &A.counts[set][map], S.prof)) {
+            binary_h1_pairs(A.maps[set] + (size_t)map * N, H, W, smem, kSmallSmemBytes, A.ps, set, map, S.prof)) {
             TL_PROF(0);
             continue;
         }
@@ -476,6 +477,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         if (!fast_one) {
             unsigned long long best = 0ull;
             uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+            bool has_nan = false;
             if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.f) & 15) == 0) {
                 const float4* f4 = reinterpret_cast<const float4*>(g.f);
 #pragma unroll 4
@@ -485,6 +487,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t m = mono32(vv[k]);
+                        has_nan |= vv[k] != vv[k];
                         lo = min(lo, m); hi = max(hi, m);
                         if (DIM == 0) {
                             unsigned long long kk = ((unsigned long long)m << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)(4 * q + k));
@@ -495,7 +498,9 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             } else {
 #pragma unroll 4
                 for (int p = tid; p < N; p += nt) {
-                    const uint32_t m = mono32(__ldg(g.f + p));
+                    const float fv = __ldg(g.f + p);
+                    const uint32_t m = mono32(fv);
+                    has_nan |= fv != fv;
                     lo = min(lo, m); hi = max(hi, m);
                     if (DIM == 0) {
                         unsigned long long k = ((unsigned long long)m << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)p);
@@ -506,21 +511,28 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
             if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
             if (DIM == 0) atomicMax(&s_argmax, best);
+            if (has_nan) s_nan = 1;
         }
         __syncthreads();
         if (!fast_one) TL_PROF(0);
+        if (!fast_one && s_nan) {  // block-uniform: the (value, position) order is undefined with a NaN
+            if (tid == 0) { int av; atomicOr(A.ps.status, kStNonFinite); ps_reserve(A.ps, set, map, 0, &av); A.ps.dsum[set][map] = 0.0; }
+            continue;
+        }
         if (!fast_one && s_lo == s_hi) {  // block-uniform
             if (tid == 0) {
-                int cnt = 0;
-                if (DIM == 0 && A.cap > 0) {
+                int avail;
+                const unsigned long long base = ps_reserve(A.ps, set, map, DIM == 0 ? 1 : 0, &avail);
+                double ds = 0.0;
+                if (DIM == 0 && avail > 0) {  // H0 keeps only the essential class (0 -> argmax = 0)
                     PairRec rec;
                     rec.cre = 0; rec.des = 0; rec.b = rec.d = __ldg(g.f);
                     rec.tb = rec.td = __int_as_float(0x7FC00000);
-                    A.pairs[set][(size_t)map * A.cap] = rec;
-                    if (A.skeys[set]) A.skeys[set][(size_t)map * A.cap] = ~0ull;
-                    cnt = 1;
+                    A.ps.arena[base] = rec;
+                    if (A.ps.skeys) A.ps.skeys[base] = ~0ull;
+                    ds = (double)cost_diag(rec.b, rec.d, A.ps.q);
                 }
-                A.counts[set][map] = cnt;
+                A.ps.dsum[set][map] = ds;
             }
             continue;
         }
@@ -616,6 +628,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             // ---- level 0a: pick pointers, min / max of the map, tie flags for level 0b
             {
                 float vlo = __int_as_float(0x7F800000), vhi = __int_as_float(0xFF800000);
+                bool nan_seen = false;
                 for (int t = 0; t < trips; ++t) {
                     const int x = wbeg + t * 128 + lane * 4;  // band-local id of the quad
                     unsigned defer = 0u;
@@ -629,6 +642,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                         const float R = c + 4 < W ? __ldg(q + 4) : 0.f;
                         vlo = fminf(vlo, fminf(fminf(M.x, M.y), fminf(M.z, M.w)));
                         vhi = fmaxf(vhi, fmaxf(fmaxf(M.x, M.y), fmaxf(M.z, M.w)));
+                        nan_seen |= (M.x != M.x) | (M.y != M.y) | (M.z != M.z) | (M.w != M.w);
                         const float m[6] = {L, M.x, M.y, M.z, M.w, R};
                         const float u[4] = {U.x, U.y, U.z, U.w}, d[4] = {D.x, D.y, D.z, D.w};
                         uint32_t pk[4];
@@ -672,12 +686,13 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 // constant-map shortcut (absent classes give all-zero ground-truth maps: no finite pair);
                 // banded maps took it in phase 0
                 if (fast_one) {
+                    if (nan_seen) s_nan = 1;
                     const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, mono32(vlo)), hi = __reduce_max_sync(0xFFFFFFFFu, mono32(vhi));
                     if (lane == 0 && wbeg < wend) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
                 }
             }
             __syncthreads();
-            if (fast_one && s_lo == s_hi) break;  // block-uniform: constant map, handled after the band loop
+            if (fast_one && (s_lo == s_hi || s_nan)) break;  // block-uniform: constant / NaN map, handled after the band loop
             // ---- level 0b: elder-linked lock-free unions for the tie-flagged nodes
             for (int w0 = warp; w0 < ((nb + 31) >> 5); w0 += nt >> 5) {
                 const unsigned bits = mask[w0];
@@ -874,8 +889,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             cid_base += Kb;
             TL_PROF(6);
             }  // bands
-            if (fast_one && s_lo == s_hi) {  // block-uniform: constant map
-                if (tid == 0) A.counts[set][map] = 0;
+            if (fast_one && (s_lo == s_hi || s_nan)) {  // block-uniform: constant map, or a NaN pixel (pairing undefined)
+                if (tid == 0) { int avail; if (s_nan) atomicOr(A.ps.status, kStNonFinite); ps_reserve(A.ps, set, map, 0, &avail); A.ps.dsum[set][map] = 0.0; }
                 TL_PROF(0);
                 continue;
             }
@@ -1094,6 +1109,10 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             TL_PROF(6);
         }
         const int K = cid_base;  // basins 1..K (0 = OUTSIDE for H1, unused for H0)
+        if ((size_t)K + 2 > S.k_stride) {  // block-uniform; only with the typical-size tables of multi-band maps
+            if (tid == 0) { int av; atomicOr(A.ps.status, kStBasins); ps_reserve(A.ps, set, map, 0, &av); A.ps.dsum[set][map] = 0.0; }
+            continue;
+        }
 
         // ---- phase B: triplet merge tree over basins
         // packed 64-bit entries when edge id + basin id fit 32 bits next to the 32-bit value (always
@@ -1172,8 +1191,6 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 for (int i = tid; i < (N * 4 + 127) / 128; i += nt) asm volatile("prefetch.global.L2 [%0];" :: "l"(nm + (size_t)i * 128));
             }
         }
-        PairRec* out = A.pairs[set] + (size_t)map * A.cap;
-        uint64_t* skeys = A.skeys[set] ? A.skeys[set] + (size_t)map * A.cap : nullptr;
         {
             auto load_entry = [&](int c, uint64_t& ekey, uint32_t& zv) {
                 if (packed) {
@@ -1215,7 +1232,13 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 for (int c = c_beg; c < c_end; ++c)
                     if ((flags >> (c - c_beg)) & 1ull) { if (lst_smem) lst16[slot] = (uint16_t)c; else zvalg[slot] = (uint32_t)c; ++slot; }
             }
+            // the map's records: one reservation in the shared arena
+            if (tid == 0) { int av; s_base = ps_reserve(A.ps, set, map, total, &av); s_count = av; }
             __syncthreads();
+            PairRec* out = A.ps.arena + s_base;
+            uint64_t* skeys = A.ps.skeys ? A.ps.skeys + s_base : nullptr;
+            const int avail = s_count;
+            double dacc = 0.0;  // sum of the points' costs to the diagonal (the matching kernel's column term)
             // 4 records per thread per trip, staged so that the global loads of the 4 records overlap; per
             // record the only dependent global accesses are the two map values that decide the edge's pixel
             for (int j0 = tid; j0 < total; j0 += 4 * nt) {
@@ -1260,17 +1283,17 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j0 + u * nt;
-                    if (j < total && j < A.cap) {
+                    if (j < avail) {
                         rec4[u].tb = rec4[u].td = __int_as_float(0x7FC00000);
                         out[j] = rec4[u];
                         if (skeys) skeys[j] = sk4[u];
+                        dacc += (double)cost_diag(rec4[u].b, rec4[u].d, A.ps.q);
                     }
                 }
             }
-            if (tid == 0) s_count = total;
+            dacc = block_sum(dacc, s_red);
+            if (tid == 0) A.ps.dsum[set][map] = dacc;
         }
-        __syncthreads();
-        if (tid == 0) A.counts[set][map] = s_count;
         TL_PROF(5);
     }
 #undef TL_PROF

@@ -1,8 +1,9 @@
 // Batched segmented LSD radix sort: one CTA per (image, class) map sorts that map's persistence
 // pairs by the filtration key of their death cell, i.e. into the order gudhi emits them
 // (cofaces_of_persistence_pairs, reached from /root/reference/octsam/models/topological_loss.py:62).
-// The emit phase of ph_kernel allocates slots with atomics, so this sort is what makes the
-// diagrams -- and therefore the matching, the loss and the gradient -- run-to-run deterministic.
+// The persistence kernels emit a map's pairs in raster order of the dying basin (deterministic, and
+// what the loss path uses as is); this sort only serves tl_persistence_pairs, whose contract is gudhi's
+// emission order.
 //
 // 8-bit digits over 64-bit keys; passes whose digit is constant over the segment are skipped.
 // Stability: every warp owns a contiguous chunk of the segment and walks it in order; within a
@@ -16,10 +17,9 @@ constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
 
 struct SortArgs {
-    PairRec* pairs[2];
-    uint64_t* skeys[2];
-    const int32_t* counts[2];
-    int n_sets, n_maps, cap;
+    PairStore ps;        // records and sort keys of every map (arena + per-map offsets / counts)
+    int n_sets, n_maps;
+    int cap;             // most pairs one map can have (scratch stride)
     // per-CTA scratch
     uint64_t* key_tmp;   // [grid][cap]
     uint32_t* idx_a;     // [grid][cap]
@@ -40,11 +40,11 @@ __global__ void __launch_bounds__(kSortThreads) seg_sort_kernel(SortArgs A) {
 
     for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
         const int set = job % A.n_sets, map = job / A.n_sets;
-        int n = A.counts[set][map];
+        int n = A.ps.counts[set][map];
         if (n > A.cap) n = A.cap;
         if (n <= 1) continue;
-        PairRec* recs = A.pairs[set] + (size_t)map * A.cap;
-        uint64_t* k0 = A.skeys[set] + (size_t)map * A.cap;
+        PairRec* recs = A.ps.arena + A.ps.offs[set][map];
+        uint64_t* k0 = A.ps.skeys + A.ps.offs[set][map];
         uint64_t* ksrc = k0; uint64_t* kdst = kt;
         uint32_t* isrc = ia; uint32_t* idst = ib;
         for (int i = tid; i < n; i += kSortThreads) ia[i] = (uint32_t)i;

@@ -12,6 +12,7 @@
 // "smaller key" always means "earlier in the scan" (edges) / "elder" (nodes).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 namespace tl {
@@ -21,6 +22,68 @@ struct __align__(8) PairRec {
     float b, d;        // diagram point gathered from the map: (f[cre], f[des])
     float tb, td;      // matched ground-truth point, NaN = matched to the diagonal (pred side only)
 };
+
+// Device status word (workspace header): sticky bits set by the kernels, folded into the loss as NaN and
+// readable through tl_status().  With the default (typical-size) workspace a pathological input can
+// exhaust the pair arena or, on maps of more than 65536 pixels, the basin tables; the worst-case
+// workspace (tl_set_option(TL_OPT_WORST_CASE_WORKSPACE, 1)) cannot overflow.
+constexpr unsigned int kStArena = 1u;      // pair arena exhausted: some maps lost pairs
+constexpr unsigned int kStBasins = 2u;     // more basins than the per-CTA tables hold (multi-band maps)
+constexpr unsigned int kStNonFinite = 4u;  // a map holds a NaN: the pairing is undefined
+
+// Where persistence pairs live: ONE record arena shared by all maps of both sets, carved with a device
+// counter (a map's pairs are contiguous; maps land in the order they finish), instead of a worst-case
+// stride of H*W/2 records per map.
+struct PairStore {
+    PairRec* arena;
+    uint64_t* skeys;               // sort key per record (death-cell order), parallel to arena; may be null
+    unsigned long long* head;      // next free record
+    unsigned long long cap;        // records in the arena
+    uint32_t* offs[2];             // [n_maps] first record of each map
+    int32_t* counts[2];            // [n_maps] records of each map
+    double* dsum[2];               // [n_maps] sum over the map's points of their cost to the diagonal
+    unsigned int* status;
+    float q;                       // exponent of the Wasserstein cost (for dsum)
+};
+
+__device__ __forceinline__ float powq(float x, float q) { return q == 2.0f ? x * x : powf(x, q); }
+// torch.cdist(p=inf) entry, then .pow(q)
+__device__ __forceinline__ float cost_pp(float b, float d, float b2, float d2, float q) {
+    return powq(fmaxf(fabsf(b - b2), fabsf(d - d2)), q);
+}
+// torch.linalg.vector_norm(D - 0.5*(x+y), inf), then .pow(q)
+__device__ __forceinline__ float cost_diag(float b, float d, float q) {
+    const float h = 0.5f * (b + d);
+    return powq(fmaxf(fabsf(b - h), fabsf(d - h)), q);
+}
+
+// deterministic block-wide sum (shuffle tree per warp, then the warps in order); s_red: 32 doubles
+__device__ __forceinline__ double block_sum(double x, double* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, o);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = x;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    return t;
+}
+
+// Reserve `total` records for one map (one thread calls this): returns the first record and how many
+// of them fit; an exhausted arena sets the status bit and truncates.
+__device__ __forceinline__ unsigned long long ps_reserve(const PairStore& ps, int set, int map, int total, int* avail) {
+    const unsigned long long base = total > 0 ? atomicAdd(ps.head, (unsigned long long)total) : 0ull;
+    int a = total;
+    if (base + (unsigned long long)total > ps.cap) {
+        a = base < ps.cap ? (int)(ps.cap - base) : 0;
+        atomicOr(ps.status, kStArena);
+    }
+    ps.offs[set][map] = (uint32_t)(base < ps.cap ? base : 0ull);
+    ps.counts[set][map] = a;
+    *avail = a;
+    return base;
+}
 
 __device__ __forceinline__ uint32_t mono32(float f) {
     uint32_t u = __float_as_uint(f);

@@ -4,6 +4,8 @@
 #include "../../include/topoloss.h"
 
 #include <cuda_runtime.h>
+#include <atomic>
+#include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -33,33 +35,59 @@ int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(TL_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
-// Optional per-kernel timing (bench.py's roofline): when enabled on this thread, tl_forward and
-// tl_backward bracket each kernel with cudaEventRecord on the caller's stream.  Events are created
-// lazily and reused; nothing is synchronised until tl_timing_read.
-constexpr int kStages = 6;        // ph, sort, match, loss, grad-zero, grad-scatter
+// Process-wide options (tl_set_option); initial values come from the environment ONCE, at load time.
+struct Options {
+    std::atomic<int> v[TL_OPT_COUNT_];
+    Options() {
+        auto env1 = [](const char* k) { const char* e = getenv(k); return e && e[0] == '1' ? 1 : 0; };
+        v[TL_OPT_FORCE_GLOBAL_KERNEL] = env1("TL_FORCE_GLOBAL");
+        v[TL_OPT_PROFILE] = env1("TL_PROFILE");
+        v[TL_OPT_NO_BINARY_PATH] = env1("TL_NO_BINARY");
+        v[TL_OPT_WORST_CASE_WORKSPACE] = env1("TL_WORST_CASE_WORKSPACE");
+    }
+};
+Options g_opt;
+inline int opt(int which) { return g_opt.v[which].load(std::memory_order_relaxed); }
+
+// Optional per-kernel timing (bench.py's roofline): while enabled, tl_forward and tl_backward bracket each
+// kernel with cudaEventRecord on the caller's stream.  Process-wide (tl_backward runs on autograd's worker
+// thread), guarded by a mutex; events are created lazily and reused; nothing is synchronised until
+// tl_timing_read.
+constexpr int kStages = 6;        // ph, (sort: unused in the loss path), match, loss, grad fill + scatter (fused), -
 constexpr int kTimingRing = 128;  // calls remembered between two reads
 struct Timing {
+    std::mutex mu;
     bool on = false;
     int n_fwd = 0, n_bwd = 0;
     cudaEvent_t ev[kTimingRing][kStages + 2] = {};
     bool have[kTimingRing] = {};
 };
-Timing g_timing;  // process-wide: tl_backward runs on autograd's worker thread
+Timing g_timing;
 
-cudaEvent_t timing_event(int call, int idx) {
-    Timing& t = g_timing;
-    if (!t.have[call]) {
-        for (int i = 0; i < kStages + 2; ++i) cudaEventCreate(&t.ev[call][i]);
-        t.have[call] = true;
+// returns the ring slot of this call (or -1 when timing is off / the ring is full); marks are recorded under the lock
+struct TimingScope {
+    int call = -1;
+    explicit TimingScope(bool fwd) {
+        std::lock_guard<std::mutex> lk(g_timing.mu);
+        if (!g_timing.on) return;
+        int& n = fwd ? g_timing.n_fwd : g_timing.n_bwd;
+        if (n < kTimingRing) {
+            call = n;
+            if (!g_timing.have[call]) {
+                for (int i = 0; i < kStages + 2; ++i) cudaEventCreate(&g_timing.ev[call][i]);
+                g_timing.have[call] = true;
+            }
+        }
+        ++n;
     }
-    return t.ev[call][idx];
-}
-#define TL_MARK(call, idx, st) do { if (g_timing.on && (call) < kTimingRing) cudaEventRecord(timing_event((call), (idx)), (st)); } while (0)
+    void mark(int idx, cudaStream_t st) const { if (call >= 0) cudaEventRecord(g_timing.ev[call][idx], st); }
+};
 
-constexpr int kPhSlots = 296;     // CTAs of the persistence kernel (2 per SM on a 148-SM B200)
-constexpr int kSmallSlots = 160;   // >= SM count: one 1024-thread CTA per SM in ph_small_kernel
-constexpr int kSortSlots = 296;
-constexpr int kMatchSlots = 296;
+constexpr int kPhSlots = 296;      // CTAs of the global-memory persistence kernel
+constexpr int kSmallSlotsMax = 160;  // per-CTA scratch slots of ph_small_kernel: one 1024-thread CTA per SM
+constexpr int kSortSlots = 64;
+constexpr int kMatchSlots = 296;   // tl_wasserstein
+constexpr int kHeavySlots = 16;    // maps whose two diagrams both exceed kSmallR points (rare)
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -69,64 +97,105 @@ int max_pairs(int H, int W, int dim) {
     return (int)(nn / 2 + 2);
 }
 
-struct Layout {
-    int M, cap, n_nodes;
-    size_t counter, counts[2], cost, tpers, coef, pairs[2], skeys[2], match1;
-    size_t T, t_stride;
-    int small;  // 1: shared-memory persistence kernel (<= 65535 nodes)
+int sm_count() {  // per call: the device may differ between calls (one process, several GPUs)
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    return v > kSmallSlotsMax ? kSmallSlotsMax : v;
+}
+
+// STATE (kept from tl_forward to tl_backward): header, per-map bookkeeping, the pair arena.
+//   header: [0] job counter (u32) | [8] arena head (u64) | [16] status (u32) | [20] heavy count (u32) |
+//           [24] match work counter (u32) | [64..127] phase cycle counters (8 x u64)
+struct StateLayout {
+    int M;
+    size_t counts[2], offs[2], dsum[2], cost, tpers, coef, heavy, arena, fixed;
+    unsigned long long arena_default;  // records tl_workspace_bytes asks for
+};
+StateLayout make_state(int M, int H, int W, int dim, int B) {
+    StateLayout L;
+    memset(&L, 0, sizeof(L));
+    L.M = M;
+    size_t o = 256;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes); return at; };
+    for (int s = 0; s < 2; ++s) L.counts[s] = take(sizeof(int32_t) * (size_t)M);
+    for (int s = 0; s < 2; ++s) L.offs[s] = take(sizeof(uint32_t) * (size_t)M);
+    for (int s = 0; s < 2; ++s) L.dsum[s] = take(sizeof(double) * (size_t)M);
+    L.cost = take(sizeof(double) * (size_t)M);
+    L.tpers = take(sizeof(double) * (size_t)M);
+    L.coef = take(sizeof(double) * (size_t)(B > 0 ? B : 1));
+    L.heavy = take(sizeof(int32_t) * (size_t)M);
+    L.arena = o;
+    L.fixed = o;
+    // Records for both sets together.  Worst case: max_pairs per map and set.  Typical: noise-like
+    // predictions give ~N/5 pairs per map (iid uniform noise: N/5.1), ground truth a handful.
+    const unsigned long long cap = (unsigned long long)max_pairs(H, W, dim);
+    // Small maps always get (close to) the worst case: memory only matters for the big ones.
+    unsigned long long typical = (unsigned long long)H * W / 5 + 64;
+    if (typical < 8192) typical = 8192;
+    L.arena_default = (unsigned long long)M * (opt(TL_OPT_WORST_CASE_WORKSPACE) ? 2 * cap : (typical < 2 * cap ? typical : 2 * cap));
+    return L;
+}
+
+// SCRATCH (only live inside one call): per-CTA tables of the persistence kernels, the heavy matching
+// path, and -- for tl_persistence_pairs -- the sort keys and the sort's buffers.
+struct ScratchLayout {
+    int cap, n_nodes, small, slots;
     size_t rootpix, zval, T2g, k_stride, elist, e_stride;
-    size_t key_tmp, idx_a, idx_b, rec_tmp;
+    size_t T, t_stride;
+    size_t skeys, key_tmp, idx_a, idx_b, rec_tmp;
     size_t v, minv, u, way, pcol, used, stride_c, stride_r;
     size_t total;
 };
-
-// Carve the workspace.  n_sets = 2 for the loss (pred + truth), 1 for tl_persistence_pairs.
-Layout make_layout(int M, int H, int W, int dim, int B) {
-    Layout L;
+ScratchLayout make_scratch(int H, int W, int dim, bool with_sort, unsigned long long arena_records) {
+    ScratchLayout L;
     memset(&L, 0, sizeof(L));
-    L.M = M;
     L.cap = max_pairs(H, W, dim);
     L.n_nodes = dim == 1 ? H * W + 1 : (H + 1) * (W + 1);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes); return at; };
-    L.counter = take(256);
-    for (int s = 0; s < 2; ++s) L.counts[s] = take(sizeof(int32_t) * (size_t)M);
-    L.cost = take(sizeof(double) * (size_t)M);
-    L.tpers = take(sizeof(double) * (size_t)M);
-    L.coef = take(sizeof(double) * (size_t)(B > 0 ? B : 1));
-    for (int s = 0; s < 2; ++s) L.pairs[s] = take(sizeof(tl::PairRec) * (size_t)M * L.cap);
-    for (int s = 0; s < 2; ++s) L.skeys[s] = take(sizeof(uint64_t) * (size_t)M * L.cap);
-    L.match1 = take(sizeof(int32_t) * (size_t)M * L.cap);
-    // shared-memory kernel: processes the map in bands of whole node rows (<= 65535 nodes each)
+    // shared-memory kernel: processes the map in bands of whole node columns (<= 65535 nodes each)
     L.small = (W + 1) <= tl::kSmallMaxRow && (long long)L.n_nodes < (1ll << 22);
+    const bool force_global = opt(TL_OPT_FORCE_GLOBAL_KERNEL) != 0;
     if (L.small) {
-        L.k_stride = align_up((size_t)L.cap + 2, 64);
-        L.rootpix = take(sizeof(uint32_t) * L.k_stride * kSmallSlots);
-        L.zval = take(sizeof(uint32_t) * L.k_stride * kSmallSlots);
-        L.T2g = take(sizeof(tl::TEntry) * L.k_stride * kSmallSlots);
-        L.e_stride = align_up((size_t)H * (W + 1) + (size_t)(H + 1) * W, 64);
-        L.elist = take(sizeof(tl::CrossEdge) * L.e_stride * kSmallSlots);
+        L.slots = sm_count();
+        // basins per map: at most cap.  Maps of more than one band (> 65536 nodes) get tables for N/4 basins
+        // unless the worst-case workspace is asked for (iid noise has N/5); overflow -> status bit + NaN loss
+        size_t k_cap = (size_t)L.cap;
+        // (tl_persistence_pairs, the parity-test boundary, always takes the worst case)
+        if (L.n_nodes > 65537 && !opt(TL_OPT_WORST_CASE_WORKSPACE) && !with_sort) k_cap = (size_t)L.n_nodes / 4 + 2;
+        L.k_stride = align_up(k_cap + 2, 64);
+        L.rootpix = take(sizeof(uint32_t) * L.k_stride * L.slots);
+        L.zval = take(sizeof(uint32_t) * L.k_stride * L.slots);
+        L.T2g = take(sizeof(tl::TEntry) * L.k_stride * L.slots);
+        // crossing edges: every node that is not a basin root owns one level-0 (non-crossing) edge, so a map
+        // has at most n_edges - (n_nodes - K) of them
+        const size_t n_edges = (size_t)H * (W + 1) + (size_t)(H + 1) * W;
+        const size_t n_real = dim == 1 ? (size_t)H * W : (size_t)(H + 1) * (W + 1);
+        L.e_stride = align_up(n_edges - n_real + L.k_stride + 64, 64);
+        if (L.e_stride > align_up(n_edges, 64)) L.e_stride = align_up(n_edges, 64);
+        L.elist = take(sizeof(tl::CrossEdge) * L.e_stride * L.slots);
     }
-    {
-        const char* fg = getenv("TL_FORCE_GLOBAL");
-        if (!L.small || (fg && fg[0] == '1')) {
-            L.t_stride = align_up(sizeof(uint64_t) * (size_t)L.n_nodes) / sizeof(uint64_t);
-            L.T = take(sizeof(uint64_t) * L.t_stride * kPhSlots);
-        }
+    if (!L.small || force_global) {
+        L.t_stride = align_up(sizeof(uint64_t) * (size_t)L.n_nodes) / sizeof(uint64_t);
+        L.T = take(sizeof(uint64_t) * L.t_stride * kPhSlots);
     }
-    L.key_tmp = take(sizeof(uint64_t) * (size_t)L.cap * kSortSlots);
-    L.idx_a = take(sizeof(uint32_t) * (size_t)L.cap * kSortSlots);
-    L.idx_b = take(sizeof(uint32_t) * (size_t)L.cap * kSortSlots);
-    L.rec_tmp = take(sizeof(tl::PairRec) * (size_t)L.cap * kSortSlots);
-    L.stride_c = align_up((size_t)2 * L.cap + 2, 32);
-    L.stride_r = align_up((size_t)L.cap + 2, 32);
-    L.v = take(sizeof(double) * L.stride_c * kMatchSlots);
-    L.minv = take(sizeof(double) * L.stride_c * kMatchSlots);
-    L.u = take(sizeof(double) * L.stride_r * kMatchSlots);
-    L.way = take(sizeof(int32_t) * L.stride_c * kMatchSlots);
-    L.pcol = take(sizeof(int32_t) * L.stride_c * kMatchSlots);
-    L.used = take(L.stride_c * kMatchSlots);
-    L.total = o;
+    if (with_sort) {
+        L.skeys = take(sizeof(uint64_t) * (size_t)arena_records);
+        L.key_tmp = take(sizeof(uint64_t) * (size_t)L.cap * kSortSlots);
+        L.idx_a = take(sizeof(uint32_t) * (size_t)L.cap * kSortSlots);
+        L.idx_b = take(sizeof(uint32_t) * (size_t)L.cap * kSortSlots);
+        L.rec_tmp = take(sizeof(tl::PairRec) * (size_t)L.cap * kSortSlots);
+    } else {
+        L.stride_c = align_up((size_t)2 * L.cap + 2, 32);
+        L.stride_r = align_up((size_t)L.cap + 2, 32);
+        L.v = take(sizeof(double) * L.stride_c * kHeavySlots);
+        L.minv = take(sizeof(double) * L.stride_c * kHeavySlots);
+        L.u = take(sizeof(double) * L.stride_r * kHeavySlots);
+        L.way = take(sizeof(int32_t) * L.stride_c * kHeavySlots);
+        L.pcol = take(sizeof(int32_t) * L.stride_c * kHeavySlots);
+        L.used = take(L.stride_c * kHeavySlots);
+    }
+    L.total = o > 0 ? o : 256;
     return L;
 }
 
@@ -142,47 +211,48 @@ int check_shape(int B, int C, int H, int W, int feat_d) {
 template <typename T>
 T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
 
-int launch_ph(const float* m0, const float* m1, int n_sets, const Layout& L, int H, int W, int dim,
-              void* ws, cudaStream_t st, bool want_sort_keys) {
+tl::PairStore pair_store(void* state, const StateLayout& L, size_t state_bytes, uint64_t* skeys, float q) {
+    tl::PairStore ps;
+    ps.arena = at<tl::PairRec>(state, L.arena);
+    ps.skeys = skeys;
+    ps.head = at<unsigned long long>(state, 8);
+    ps.cap = (state_bytes - L.arena) / sizeof(tl::PairRec);
+    if (ps.cap > 0xFFFFFFFFull) ps.cap = 0xFFFFFFFFull;  // offsets are 32-bit
+    for (int s = 0; s < 2; ++s) {
+        ps.offs[s] = at<uint32_t>(state, L.offs[s]);
+        ps.counts[s] = at<int32_t>(state, L.counts[s]);
+        ps.dsum[s] = at<double>(state, L.dsum[s]);
+    }
+    ps.status = at<unsigned int>(state, 16);
+    ps.q = q;
+    return ps;
+}
+
+int launch_ph(const float* m0, const float* m1, int n_sets, int M, const tl::PairStore& ps, const ScratchLayout& L, int H, int W,
+              int dim, void* state, void* scratch, cudaStream_t st) {
     tl::PhArgs a;
     a.maps[0] = m0; a.maps[1] = m1;
-    for (int s = 0; s < 2; ++s) {
-        a.pairs[s] = at<tl::PairRec>(ws, L.pairs[s]);
-        a.skeys[s] = want_sort_keys ? at<uint64_t>(ws, L.skeys[s]) : nullptr;
-        a.counts[s] = at<int32_t>(ws, L.counts[s]);
-    }
-    a.n_sets = n_sets; a.n_maps = L.M; a.H = H; a.W = W; a.cap = L.cap;
+    a.ps = ps;
+    a.n_sets = n_sets; a.n_maps = M; a.H = H; a.W = W; a.cap = L.cap;
     a.magic_W = tl::FastDiv::magic_of((uint32_t)W); a.magic_GW = tl::FastDiv::magic_of((uint32_t)(2 * W + 1));
     a.magic_VW = tl::FastDiv::magic_of((uint32_t)(W + 1));
-    a.T = at<uint64_t>(ws, L.T); a.t_stride = L.t_stride;
-    a.job_counter = at<unsigned int>(ws, L.counter);
-    TL_CUDA(cudaMemsetAsync(a.job_counter, 0, 256, st));
-    long long jobs = (long long)n_sets * L.M;
-    int grid = (int)(jobs < kPhSlots ? jobs : kPhSlots);
-    // TL_FORCE_GLOBAL=1 (tests) routes every shape through the global-memory kernel, which otherwise only
-    // serves maps wider than kSmallMaxRow
-    const char* fg = getenv("TL_FORCE_GLOBAL");
-    const bool use_small = L.small && !(fg && fg[0] == '1');
+    a.T = at<uint64_t>(scratch, L.T); a.t_stride = L.t_stride;
+    a.job_counter = at<unsigned int>(state, 0);
+    TL_CUDA(cudaMemsetAsync(state, 0, 256, st));  // counters, arena head, status, phase counters
+    long long jobs = (long long)n_sets * M;
+    // TL_OPT_FORCE_GLOBAL_KERNEL (tests) routes every shape through the global-memory kernel, which otherwise
+    // only serves maps wider than kSmallMaxRow
+    const bool use_small = L.small && !opt(TL_OPT_FORCE_GLOBAL_KERNEL);
     if (use_small) {
-        static int n_sm = 0;
-        if (n_sm == 0) {
-            int dev = 0, v = 0;
-            TL_CUDA(cudaGetDevice(&dev));
-            TL_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
-            n_sm = v > 0 ? v : 148;
-        }
-        if (grid > n_sm) grid = n_sm;  // one 1024-thread CTA per SM, work handed out dynamically
-        if (grid > kSmallSlots) grid = kSmallSlots;
+        int grid = (int)(jobs < L.slots ? jobs : L.slots);  // one 1024-thread CTA per SM, work handed out dynamically
         tl::PhSmallArgs sa;
         sa.base = a;
-        sa.rootpix = at<uint32_t>(ws, L.rootpix); sa.zval = at<uint32_t>(ws, L.zval);
-        sa.T2g = at<tl::TEntry>(ws, L.T2g);
+        sa.rootpix = at<uint32_t>(scratch, L.rootpix); sa.zval = at<uint32_t>(scratch, L.zval);
+        sa.T2g = at<tl::TEntry>(scratch, L.T2g);
         sa.k_stride = L.k_stride;
-        sa.elist = at<tl::CrossEdge>(ws, L.elist); sa.e_stride = L.e_stride;
-        const char* pe = getenv("TL_PROFILE");
-        sa.prof = (pe && pe[0] == '1') ? at<unsigned long long>(ws, L.counter) + 8 : nullptr;
-        const char* nb = getenv("TL_NO_BINARY");
-        sa.binary_path = !(nb && nb[0] == '1');
+        sa.elist = at<tl::CrossEdge>(scratch, L.elist); sa.e_stride = L.e_stride;
+        sa.prof = opt(TL_OPT_PROFILE) ? at<unsigned long long>(state, 64) : nullptr;
+        sa.binary_path = !opt(TL_OPT_NO_BINARY_PATH);
         if (dim == 1) {
             TL_CUDA(cudaFuncSetAttribute(tl::ph_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl::kSmallSmemBytes));
             tl::ph_small_kernel<1><<<grid, tl::kPhThreads, tl::kSmallSmemBytes, st>>>(sa);
@@ -190,27 +260,11 @@ int launch_ph(const float* m0, const float* m1, int n_sets, const Layout& L, int
             TL_CUDA(cudaFuncSetAttribute(tl::ph_small_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl::kSmallSmemBytes));
             tl::ph_small_kernel<0><<<grid, tl::kPhThreads, tl::kSmallSmemBytes, st>>>(sa);
         }
-    } else if (dim == 1) tl::ph_kernel<1><<<grid, tl::kPhThreads, 0, st>>>(a);
-    else tl::ph_kernel<0><<<grid, tl::kPhThreads, 0, st>>>(a);
-    TL_CUDA(cudaGetLastError());
-    return TL_OK;
-}
-
-int launch_sort(int n_sets, const Layout& L, void* ws, cudaStream_t st) {
-    tl::SortArgs a;
-    for (int s = 0; s < 2; ++s) {
-        a.pairs[s] = at<tl::PairRec>(ws, L.pairs[s]);
-        a.skeys[s] = at<uint64_t>(ws, L.skeys[s]);
-        a.counts[s] = at<int32_t>(ws, L.counts[s]);
+    } else {
+        const int grid = (int)(jobs < kPhSlots ? jobs : kPhSlots);
+        if (dim == 1) tl::ph_kernel<1><<<grid, tl::kPhThreads, 0, st>>>(a);
+        else tl::ph_kernel<0><<<grid, tl::kPhThreads, 0, st>>>(a);
     }
-    a.n_sets = n_sets; a.n_maps = L.M; a.cap = L.cap;
-    a.key_tmp = at<uint64_t>(ws, L.key_tmp);
-    a.idx_a = at<uint32_t>(ws, L.idx_a);
-    a.idx_b = at<uint32_t>(ws, L.idx_b);
-    a.rec_tmp = at<tl::PairRec>(ws, L.rec_tmp);
-    long long jobs = (long long)n_sets * L.M;
-    int grid = (int)(jobs < kSortSlots ? jobs : kSortSlots);
-    tl::seg_sort_kernel<<<grid, tl::kSortThreads, 0, st>>>(a);
     TL_CUDA(cudaGetLastError());
     return TL_OK;
 }
@@ -230,16 +284,38 @@ int tl_version(void) { return TL_ABI_VERSION; }
 
 const char* tl_last_error(void) { return g_err; }
 
+int tl_set_option(int which, int value) {
+    if (which < 0 || which >= TL_OPT_COUNT_) return fail(TL_ERR_ARG, "unknown option %d", which);
+    g_opt.v[which].store(value, std::memory_order_relaxed);
+    return TL_OK;
+}
+
+int tl_get_option(int which) {
+    if (which < 0 || which >= TL_OPT_COUNT_) return fail(TL_ERR_ARG, "unknown option %d", which);
+    return opt(which);
+}
+
 /* Debug aid (not part of the hot path): copies the 8 phase cycle counters that the persistence
- * kernel accumulates when the environment has TL_PROFILE=1.  Synchronises the device. */
-int tl_debug_profile(const void* ws, unsigned long long* host_out8) {
-    if (!ws || !host_out8) return fail(TL_ERR_ARG, "null pointer");
+ * kernel accumulates while TL_OPT_PROFILE is set.  Synchronises the device. */
+int tl_debug_profile(const void* state, unsigned long long* host_out8) {
+    if (!state || !host_out8) return fail(TL_ERR_ARG, "null pointer");
     TL_CUDA(cudaDeviceSynchronize());
-    TL_CUDA(cudaMemcpy(host_out8, static_cast<const char*>(ws) + 64, 64, cudaMemcpyDeviceToHost));
+    TL_CUDA(cudaMemcpy(host_out8, static_cast<const char*>(state) + 64, 64, cudaMemcpyDeviceToHost));
+    return TL_OK;
+}
+
+int tl_status(const void* state, int* host_status, void* stream) {
+    if (!state || !host_status) return fail(TL_ERR_ARG, "null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned int v = 0;
+    TL_CUDA(cudaMemcpyAsync(&v, static_cast<const char*>(state) + 16, 4, cudaMemcpyDeviceToHost, st));
+    TL_CUDA(cudaStreamSynchronize(st));
+    *host_status = (int)v;
     return TL_OK;
 }
 
 int tl_timing_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_timing.mu);
     g_timing.on = on != 0;
     g_timing.n_fwd = g_timing.n_bwd = 0;
     return TL_OK;
@@ -247,6 +323,7 @@ int tl_timing_enable(int on) {
 
 int tl_timing_read(float* ms_sum6, int* n_calls) {
     if (!ms_sum6 || !n_calls) return fail(TL_ERR_ARG, "null pointer");
+    std::lock_guard<std::mutex> lk(g_timing.mu);
     Timing& t = g_timing;
     for (int i = 0; i < kStages; ++i) ms_sum6[i] = 0.f;
     const int nf = t.n_fwd < kTimingRing ? t.n_fwd : kTimingRing;
@@ -278,83 +355,95 @@ int tl_max_pairs(int H, int W, int dim) {
     return max_pairs(H, W, dim);
 }
 
-int tl_workspace_bytes(int B, int C, int H, int W, int feat_d, size_t* bytes) {
-    if (!bytes) return fail(TL_ERR_ARG, "bytes is null");
+int tl_workspace_bytes(int B, int C, int H, int W, int feat_d, size_t* state_bytes, size_t* scratch_bytes) {
+    if (!state_bytes || !scratch_bytes) return fail(TL_ERR_ARG, "null pointer");
     int rc = check_shape(B, C, H, W, feat_d);
     if (rc != TL_OK) return rc;
-    *bytes = make_layout(B * C, H, W, feat_d, B).total;
+    const StateLayout S = make_state(B * C, H, W, feat_d, B);
+    *state_bytes = S.fixed + (size_t)S.arena_default * sizeof(tl::PairRec);
+    *scratch_bytes = make_scratch(H, W, feat_d, false, 0).total;
     return TL_OK;
 }
 
 int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W, int feat_d, float q,
-               float lamda, int loss_r, int B_global, void* ws, size_t ws_bytes, float* loss_out,
-               void* stream) {
+               float lamda, int loss_r, int B_global, void* state, size_t state_bytes, void* scratch,
+               size_t scratch_bytes, float* loss_out, void* stream) {
     int rc = check_shape(B, C, H, W, feat_d);
     if (rc != TL_OK) return rc;
-    if (!pred || !truth || !ws || !loss_out) return fail(TL_ERR_ARG, "null pointer");
+    if (!pred || !truth || !state || !scratch || !loss_out) return fail(TL_ERR_ARG, "null pointer");
     if (!(q > 0.f)) return fail(TL_ERR_ARG, "loss_q must be positive");
     if (B_global <= 0) B_global = B;
-    const Layout L = make_layout(B * C, H, W, feat_d, B);
-    if (ws_bytes < L.total) return fail(TL_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, L.total);
+    const int M = B * C;
+    const StateLayout S = make_state(M, H, W, feat_d, B);
+    const ScratchLayout L = make_scratch(H, W, feat_d, false, 0);
+    if (state_bytes < S.fixed + sizeof(tl::PairRec)) return fail(TL_ERR_WORKSPACE, "state %zu < %zu bytes", state_bytes, S.fixed + sizeof(tl::PairRec));
+    if (scratch_bytes < L.total) return fail(TL_ERR_WORKSPACE, "scratch %zu < %zu bytes", scratch_bytes, L.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const tl::PairStore ps = pair_store(state, S, state_bytes, nullptr, q);
 
-    const int call = g_timing.n_fwd;
-    TL_MARK(call, 0, st);
+    const TimingScope tm(true);
+    tm.mark(0, st);
     // pairs leave the persistence kernel in a deterministic (raster) order, so the matching needs no
     // sort; the segmented sort only serves tl_persistence_pairs (gudhi's emission order)
-    rc = launch_ph(pred, truth, 2, L, H, W, feat_d, ws, st, false);
+    rc = launch_ph(pred, truth, 2, M, ps, L, H, W, feat_d, state, scratch, st);
     if (rc != TL_OK) return rc;
-    TL_MARK(call, 1, st);
-    TL_MARK(call, 2, st);
+    tm.mark(1, st);
+    tm.mark(2, st);
 
-    tl::MatchArgs m;
-    m.d1 = tl::Diagrams{reinterpret_cast<const char*>(at<tl::PairRec>(ws, L.pairs[0])) + offsetof(tl::PairRec, b),
-                        (int)sizeof(tl::PairRec), nullptr, at<int32_t>(ws, L.counts[0]), L.cap};
-    m.d2 = tl::Diagrams{reinterpret_cast<const char*>(at<tl::PairRec>(ws, L.pairs[1])) + offsetof(tl::PairRec, b),
-                        (int)sizeof(tl::PairRec), nullptr, at<int32_t>(ws, L.counts[1]), L.cap};
-    m.n_diag = L.M; m.q = q; m.loss_r = loss_r;
-    m.cost = at<double>(ws, L.cost); m.tpers = at<double>(ws, L.tpers);
-    m.match1 = at<int32_t>(ws, L.match1);
-    m.fill1 = at<tl::PairRec>(ws, L.pairs[0]);
-    fill_match_scratch(m, ws, L.v, L.minv, L.u, L.way, L.pcol, L.used, L.stride_c, L.stride_r);
-    m.counter = at<unsigned int>(ws, L.counter) + 32;  // byte 128 of the counter block launch_ph zeroed
-    tl::match_kernel<<<L.M < kMatchSlots ? L.M : kMatchSlots, tl::kMatchThreads, 0, st>>>(m);
+    tl::MatchFwdArgs mf;
+    mf.ps = ps; mf.n_maps = M; mf.loss_r = loss_r; mf.q = q;
+    mf.cost = at<double>(state, S.cost); mf.tpers = at<double>(state, S.tpers);
+    mf.heavy = at<int32_t>(state, S.heavy); mf.n_heavy = at<unsigned int>(state, 20);
+    mf.counter = at<unsigned int>(state, 24);
+    tl::match_small_kernel<<<M < kMatchSlots ? M : kMatchSlots, tl::kMatchThreads, 0, st>>>(mf);
     TL_CUDA(cudaGetLastError());
-    TL_MARK(call, 3, st);
+    {   // maps with two large diagrams (none for segmentation ground truth): general kernel, global scratch
+        tl::MatchArgs m;
+        const char* recs = reinterpret_cast<const char*>(ps.arena) + offsetof(tl::PairRec, b);
+        m.d1 = tl::Diagrams{recs, (int)sizeof(tl::PairRec), nullptr, ps.offs[0], ps.counts[0]};
+        m.d2 = tl::Diagrams{recs, (int)sizeof(tl::PairRec), nullptr, ps.offs[1], ps.counts[1]};
+        m.n_diag = M; m.q = q; m.loss_r = 0;
+        m.cost = mf.cost; m.tpers = nullptr; m.match1 = nullptr; m.fill1 = ps.arena;
+        m.list = mf.heavy; m.n_list = mf.n_heavy;
+        fill_match_scratch(m, scratch, L.v, L.minv, L.u, L.way, L.pcol, L.used, L.stride_c, L.stride_r);
+        m.counter = nullptr;
+        tl::match_kernel<<<M < kHeavySlots ? M : kHeavySlots, tl::kMatchThreads, 0, st>>>(m);
+        TL_CUDA(cudaGetLastError());
+    }
+    tm.mark(3, st);
 
     tl::LossArgs la;
-    la.cost = m.cost; la.tpers = m.tpers; la.B = B; la.C = C; la.B_global = B_global; la.loss_r = loss_r;
-    la.q = q; la.lamda = lamda; la.loss_out = loss_out; la.coef = at<double>(ws, L.coef);
+    la.cost = mf.cost; la.tpers = mf.tpers; la.B = B; la.C = C; la.B_global = B_global; la.loss_r = loss_r;
+    la.q = q; la.lamda = lamda; la.loss_out = loss_out; la.coef = at<double>(state, S.coef);
+    la.status = ps.status;
     tl::loss_kernel<<<1, 256, 0, st>>>(la);
     TL_CUDA(cudaGetLastError());
-    TL_MARK(call, 4, st);
-    if (g_timing.on) ++g_timing.n_fwd;
+    tm.mark(4, st);
     return TL_OK;
 }
 
-int tl_backward(const float* grad_loss, const void* ws, size_t ws_bytes, int B, int C, int H, int W,
-                   int feat_d, float q, float lamda, int loss_r, int B_global, float* grad_pred, void* stream) {
+int tl_backward(const float* grad_loss, const void* state, size_t state_bytes, int B, int C, int H, int W,
+                int feat_d, float q, float lamda, int loss_r, int B_global, float* grad_pred, void* stream) {
     int rc = check_shape(B, C, H, W, feat_d);
     if (rc != TL_OK) return rc;
-    if (!ws || !grad_pred) return fail(TL_ERR_ARG, "null pointer");
+    if (!state || !grad_pred) return fail(TL_ERR_ARG, "null pointer");
     if (B_global <= 0) B_global = B;
-    const Layout L = make_layout(B * C, H, W, feat_d, B);
-    if (ws_bytes < L.total) return fail(TL_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, L.total);
+    const int M = B * C;
+    const StateLayout S = make_state(M, H, W, feat_d, B);
+    if (state_bytes < S.fixed + sizeof(tl::PairRec)) return fail(TL_ERR_WORKSPACE, "state %zu < %zu bytes", state_bytes, S.fixed + sizeof(tl::PairRec));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    void* w = const_cast<void*>(ws);
-    const int call = g_timing.n_bwd;
-    TL_MARK(call, 5, st);
-    TL_CUDA(cudaMemsetAsync(grad_pred, 0, sizeof(float) * (size_t)B * C * H * W, st));
-    TL_MARK(call, 6, st);
+    void* w = const_cast<void*>(state);
+    const TimingScope tm(false);
+    tm.mark(5, st);
+    tm.mark(6, st);
     tl::GradArgs g;
-    g.pairs = at<tl::PairRec>(w, L.pairs[0]); g.counts = at<int32_t>(w, L.counts[0]);
-    g.coef = at<double>(w, L.coef); g.grad_loss = grad_loss;
-    g.M = L.M; g.C = C; g.cap = L.cap; g.N = H * W; g.B_global = B_global; g.loss_r = loss_r;
+    g.arena = at<tl::PairRec>(w, S.arena); g.offs = at<uint32_t>(w, S.offs[0]); g.counts = at<int32_t>(w, S.counts[0]);
+    g.coef = at<double>(w, S.coef); g.grad_loss = grad_loss;
+    g.M = M; g.C = C; g.N = H * W; g.B_global = B_global; g.loss_r = loss_r;
     g.q = q; g.lamda = lamda; g.grad_pred = grad_pred;
-    tl::grad_kernel<<<L.M < 1184 ? L.M : 1184, 256, 0, st>>>(g);
+    tl::grad_kernel<<<M < 1184 ? M : 1184, 512, 0, st>>>(g);
     TL_CUDA(cudaGetLastError());
-    TL_MARK(call, 7, st);
-    if (g_timing.on) ++g_timing.n_bwd;
+    tm.mark(7, st);
     return TL_OK;
 }
 
@@ -362,38 +451,69 @@ int tl_backward(const float* grad_loss, const void* ws, size_t ws_bytes, int B, 
 
 namespace {
 
-__global__ void export_pairs_kernel(const tl::PairRec* recs, const int32_t* cnt, int n_maps, int cap_in,
-                                    int32_t* pairs, int cap_out, int32_t* counts) {
+__global__ void export_pairs_kernel(tl::PairStore ps, int n_maps, int32_t* pairs, int cap_out, int32_t* counts) {
     for (int map = blockIdx.x; map < n_maps; map += gridDim.x) {
-        const int n = cnt[map];
+        const int n = ps.counts[0][map];
         if (threadIdx.x == 0) counts[map] = n;
-        const int lim = min(min(n, cap_in), cap_out);
+        const tl::PairRec* recs = ps.arena + ps.offs[0][map];
+        const int lim = min(n, cap_out);
         for (int i = threadIdx.x; i < lim; i += blockDim.x) {
-            const tl::PairRec r = recs[(size_t)map * cap_in + i];
+            const tl::PairRec r = recs[i];
             pairs[((size_t)map * cap_out + i) * 2] = r.cre;
             pairs[((size_t)map * cap_out + i) * 2 + 1] = r.des;
         }
     }
 }
 
+// tl_persistence_pairs keeps everything in ONE buffer: [state | scratch]
+struct PairsLayout { StateLayout S; ScratchLayout L; size_t state_bytes, scratch_off, total; };
+PairsLayout make_pairs_layout(int n_maps, int H, int W, int dim) {
+    PairsLayout P;
+    P.S = make_state(n_maps, H, W, dim, n_maps);
+    // one set only, and the caller may look at pathological maps: worst-case record count, capped at 2^32 - 1
+    unsigned long long recs = (unsigned long long)n_maps * (unsigned long long)max_pairs(H, W, dim);
+    if (!opt(TL_OPT_WORST_CASE_WORKSPACE) && recs > (1ull << 28)) recs = 1ull << 28;  // 6 GiB of records
+    if (recs > 0xFFFFFFFFull) recs = 0xFFFFFFFFull;
+    P.state_bytes = align_up(P.S.fixed + (size_t)recs * sizeof(tl::PairRec));
+    P.L = make_scratch(H, W, dim, true, recs);
+    P.scratch_off = P.state_bytes;
+    P.total = P.state_bytes + P.L.total;
+    return P;
+}
+
 }  // namespace
 
 extern "C" {
+
+int tl_pairs_workspace_bytes(int n_maps, int H, int W, int dim, size_t* bytes) {
+    if (!bytes) return fail(TL_ERR_ARG, "bytes is null");
+    int rc = check_shape(n_maps, 1, H, W, dim);
+    if (rc != TL_OK) return rc;
+    *bytes = make_pairs_layout(n_maps, H, W, dim).total;
+    return TL_OK;
+}
 
 int tl_persistence_pairs(const float* maps, int n_maps, int H, int W, int dim, void* ws, size_t ws_bytes,
                          int32_t* pairs, int cap, int32_t* counts, void* stream) {
     int rc = check_shape(n_maps, 1, H, W, dim);
     if (rc != TL_OK) return rc;
     if (!maps || !ws || !pairs || !counts || cap <= 0) return fail(TL_ERR_ARG, "null pointer or cap <= 0");
-    const Layout L = make_layout(n_maps, H, W, dim, n_maps);
-    if (ws_bytes < L.total) return fail(TL_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, L.total);
+    const PairsLayout P = make_pairs_layout(n_maps, H, W, dim);
+    if (ws_bytes < P.total) return fail(TL_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, P.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rc = launch_ph(maps, nullptr, 1, L, H, W, dim, ws, st, true);
+    void* scratch = static_cast<char*>(ws) + P.scratch_off;
+    const tl::PairStore ps = pair_store(ws, P.S, P.state_bytes, at<uint64_t>(scratch, P.L.skeys), 2.0f);
+    rc = launch_ph(maps, nullptr, 1, n_maps, ps, P.L, H, W, dim, ws, scratch, st);
     if (rc != TL_OK) return rc;
-    rc = launch_sort(1, L, ws, st);
-    if (rc != TL_OK) return rc;
-    export_pairs_kernel<<<n_maps < 1184 ? n_maps : 1184, 256, 0, st>>>(
-        at<tl::PairRec>(ws, L.pairs[0]), at<int32_t>(ws, L.counts[0]), n_maps, L.cap, pairs, cap, counts);
+    tl::SortArgs a;
+    a.ps = ps; a.n_sets = 1; a.n_maps = n_maps; a.cap = P.L.cap;
+    a.key_tmp = at<uint64_t>(scratch, P.L.key_tmp);
+    a.idx_a = at<uint32_t>(scratch, P.L.idx_a);
+    a.idx_b = at<uint32_t>(scratch, P.L.idx_b);
+    a.rec_tmp = at<tl::PairRec>(scratch, P.L.rec_tmp);
+    tl::seg_sort_kernel<<<n_maps < kSortSlots ? n_maps : kSortSlots, tl::kSortThreads, 0, st>>>(a);
+    TL_CUDA(cudaGetLastError());
+    export_pairs_kernel<<<n_maps < 1184 ? n_maps : 1184, 256, 0, st>>>(ps, n_maps, pairs, cap, counts);
     TL_CUDA(cudaGetLastError());
     return TL_OK;
 }
@@ -427,10 +547,10 @@ int tl_wasserstein(const float* D1, const int32_t* off1, const float* D2, const 
     const size_t oway = take(sizeof(int32_t) * sc * slots), opcol = take(sizeof(int32_t) * sc * slots);
     const size_t oused = take(sc * slots);
     tl::MatchArgs m;
-    m.d1 = tl::Diagrams{reinterpret_cast<const char*>(D1), 8, off1, nullptr, 0};
-    m.d2 = tl::Diagrams{reinterpret_cast<const char*>(D2), 8, off2, nullptr, 0};
+    m.d1 = tl::Diagrams{reinterpret_cast<const char*>(D1), 8, off1, nullptr, nullptr};
+    m.d2 = tl::Diagrams{reinterpret_cast<const char*>(D2), 8, off2, nullptr, nullptr};
     m.n_diag = n_diag; m.q = q; m.loss_r = 0; m.cost = cost; m.tpers = nullptr; m.match1 = match1; m.fill1 = nullptr;
-    m.counter = nullptr;
+    m.counter = nullptr; m.list = nullptr; m.n_list = nullptr;
     fill_match_scratch(m, ws, ov, ominv, ou, oway, opcol, oused, sc, sr);
     tl::match_kernel<<<slots, tl::kMatchThreads, 0, static_cast<cudaStream_t>(stream)>>>(m);
     TL_CUDA(cudaGetLastError());

@@ -14,10 +14,12 @@ CUDA device and the library must be built, otherwise the call raises.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -26,10 +28,83 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def _workspace(B: int, C: int, H: int, W: int, feat_d: int, device) -> torch.Tensor:
-    n = ctypes.c_size_t(0)
-    _lib.check(_lib.lib().tl_workspace_bytes(B, C, H, W, feat_d, ctypes.byref(n)), "tl_workspace_bytes")
-    return torch.empty(n.value, dtype=torch.uint8, device=device)
+_SCRATCH = {}        # (device index, stream handle) -> uint8 tensor, grown on demand
+_ARENA_FACTOR = float(os.environ.get("TL_ARENA_FACTOR", "1.0"))
+
+
+def set_arena_factor(factor: float) -> None:
+    """Scale the pair arena of every later call (1.0 = room for ~H*W/5 pairs per map; see
+    ``tl_workspace_bytes``).  Raise it when ``check_status`` reports an exhausted arena."""
+    global _ARENA_FACTOR
+    _ARENA_FACTOR = max(1.0, float(factor))
+
+
+def _buffers(B: int, C: int, H: int, W: int, feat_d: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(state, scratch) for one tl_forward: ``state`` is fresh (tl_backward reads it), ``scratch`` is one
+    cached buffer per (device, stream) -- calls on one stream run one after the other."""
+    ns, nc = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    _lib.check(_lib.lib().tl_workspace_bytes(B, C, H, W, feat_d, ctypes.byref(ns), ctypes.byref(nc)), "tl_workspace_bytes")
+    state = torch.empty(int(ns.value * _ARENA_FACTOR), dtype=torch.uint8, device=device)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    scratch = _SCRATCH.get(key)
+    if scratch is None or scratch.numel() < nc.value:
+        scratch = _SCRATCH[key] = torch.empty(nc.value, dtype=torch.uint8, device=device)
+    return state, scratch
+
+
+class _StatusRing:
+    """Deferred check of the device status word: every forward copies it (4 bytes, asynchronously) into a
+    pinned slot; the next call into this module looks at the slots whose copy has finished and raises if a
+    kernel reported an overflow or a NaN map.  The loss of that call is already NaN, so nothing is silent."""
+    SLOTS = 64
+
+    def __init__(self):
+        self.host = torch.zeros(self.SLOTS, dtype=torch.int32).pin_memory()
+        self.events = [None] * self.SLOTS
+        self.next = 0
+
+    def post(self, state: torch.Tensor, device) -> None:
+        i = self.next
+        self.next = (i + 1) % self.SLOTS
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+            self._raise_if_set(i)
+        self.host[i:i + 1].copy_(state[16:20].view(torch.int32), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self.events[i] = ev
+
+    def _raise_if_set(self, i: int) -> None:
+        v = int(self.host[i])
+        self.events[i] = None
+        self.host[i] = 0
+        if v:
+            why = "; ".join(msg for bit, msg in _lib.STATUS_BITS.items() if v & bit)
+            raise RuntimeError(f"topo_loss: an earlier call reported status {v}: {why} (its loss was NaN)")
+
+    def poll(self, sync: bool = False) -> None:
+        for i, ev in enumerate(self.events):
+            if ev is not None and (sync or ev.query()):
+                if sync:
+                    ev.synchronize()
+                self._raise_if_set(i)
+
+
+_STATUS = {}
+
+
+def _status_ring(device) -> _StatusRing:
+    r = _STATUS.get(device.index)
+    if r is None:
+        r = _STATUS[device.index] = _StatusRing()
+    return r
+
+
+def check_status(sync: bool = True) -> None:
+    """Raise if any earlier ``topo_loss`` call on this process reported a device-side problem
+    (``sync=True`` waits for the outstanding status copies first)."""
+    for ring in _STATUS.values():
+        ring.poll(sync)
 
 
 class _TopoLossFn(torch.autograd.Function):
@@ -41,22 +116,28 @@ class _TopoLossFn(torch.autograd.Function):
     def forward(ctx, pred, truth, lamda, feat_d, loss_q, loss_r, global_batch):
         B, C, H, W = pred.shape
         dev = pred.device
+        ring = _status_ring(dev)
+        ring.poll()
         with torch.cuda.device(dev):
-            ws = _workspace(B, C, H, W, feat_d, dev)
+            state, scratch = _buffers(B, C, H, W, feat_d, dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             rc = _lib.lib().tl_forward(pred.data_ptr(), truth.data_ptr(), B, C, H, W, feat_d, float(loss_q),
-                                       float(lamda), int(bool(loss_r)), int(global_batch), ws.data_ptr(),
-                                       ws.numel(), loss.data_ptr(), _stream_ptr(dev))
-        _lib.check(rc, "tl_forward")
-        ctx.ws = ws
+                                       float(lamda), int(bool(loss_r)), int(global_batch), state.data_ptr(),
+                                       state.numel(), scratch.data_ptr(), scratch.numel(), loss.data_ptr(),
+                                       _stream_ptr(dev))
+            _lib.check(rc, "tl_forward")
+            ring.post(state, dev)
+        ctx.ws = state  # header + bookkeeping + pair arena; the per-CTA scratch is not kept
         ctx.args = (B, C, H, W, feat_d, float(loss_q), float(lamda), int(bool(loss_r)), int(global_batch))
         ctx.pred_meta = (pred.dtype, dev)
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         B, C, H, W, feat_d, q, lamda, loss_r, gb = ctx.args
         dtype, dev = ctx.pred_meta
+        _status_ring(dev).poll()
         with torch.cuda.device(dev):
             g = grad_out.to(device=dev, dtype=torch.float32).contiguous()
             grad_pred = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
@@ -142,6 +223,7 @@ class _ResampleFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
         n, H, W, S, sig = ctx.meta
@@ -183,6 +265,7 @@ class _PostprocessFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         shape, n, Hs, Ws, T, rh, rw, oh, ow = ctx.meta
         dev = g.device
@@ -247,8 +330,10 @@ _COPY_STREAMS = {}
 
 def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=2, loss_r=False, *,
                         device=None, chunks=4, want_grad=True):
-    """``topo_loss`` for inputs that live in (pinned) HOST memory: forward + backward with the
-    host->device copies pipelined against the kernels.
+    """``topo_loss`` for inputs that live in pinned HOST memory: forward + backward with the
+    host->device copies pipelined against the kernels.  ``true_host`` may be ``uint8``: one-hot / component
+    masks are {0, 1} (the reference builds them on the CPU, training_utils.py:413, :432), so they can cross
+    PCIe as bytes and be widened on the device (5 instead of 8 bytes per pixel and step).
 
     The batch is cut into ``chunks`` groups of whole images; group i+1 is copied on a side stream
     while group i runs ``tl_forward`` / ``tl_backward`` (with ``B_global = B`` so the partial losses
@@ -263,8 +348,13 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
         raise ValueError("topo_loss_from_host takes maps at their final resolution (interp=0)")
     if pred_host.shape != true_host.shape or pred_host.dim() != 4:
         raise ValueError("expected two [B, C, H, W] tensors of the same shape")
-    if pred_host.dtype != torch.float32 or true_host.dtype != torch.float32:
-        raise ValueError("topo_loss expects float32 maps")
+    if pred_host.dtype != torch.float32 or true_host.dtype not in (torch.float32, torch.uint8):
+        raise ValueError("topo_loss expects a float32 prediction and float32 (or uint8 {0, 1}) ground truth")
+    if pred_host.is_cuda or true_host.is_cuda:
+        raise ValueError("topo_loss_from_host takes HOST tensors (use topo_loss for device tensors)")
+    if not (pred_host.is_pinned() and true_host.is_pinned()):
+        raise ValueError("topo_loss_from_host needs pinned host tensors (tensor.pin_memory()): a pageable "
+                         "source makes the copies synchronous and the copy / kernel overlap disappears")
     if feat_d not in (0, 1):
         raise ValueError("feat_d must be 0 or 1 for 2-D maps (the reference call site uses feat_d=1)")
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -273,11 +363,15 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
     B, C, H, W = pred_host.shape
     if H < 2 or W < 2 or (B == 1 and C == 1):
         raise ValueError("unsupported shape (see topo_loss)")
+    orig_shape = None
     if B == 1:  # the reference's .squeeze() quirk: every channel is its own image
+        orig_shape = (B, C, H, W)
         pred_host, true_host = pred_host.reshape(C, 1, H, W), true_host.reshape(C, 1, H, W)
         B, C = C, 1
     L = _lib.lib()
     chunks = max(1, min(int(chunks), B))
+    ring = _status_ring(dev)
+    ring.poll()
     with torch.cuda.device(dev):
         cur = torch.cuda.current_stream(dev)
         side = _COPY_STREAMS.get(dev.index)
@@ -286,6 +380,7 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
         side.wait_stream(cur)
         pred = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
         truth = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+        truth_u8 = torch.empty((B, C, H, W), dtype=torch.uint8, device=dev) if true_host.dtype == torch.uint8 else None
         grad = torch.empty((B, C, H, W), dtype=torch.float32, device=dev) if want_grad else None
         parts = torch.empty((chunks,), dtype=torch.float32, device=dev)
         bounds = [(i * B) // chunks for i in range(chunks + 1)]
@@ -294,25 +389,35 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
             for i in range(chunks):
                 a, b = bounds[i], bounds[i + 1]
                 pred[a:b].copy_(pred_host[a:b], non_blocking=True)
-                truth[a:b].copy_(true_host[a:b], non_blocking=True)
+                if truth_u8 is not None:  # {0, 1} masks travel as bytes and are widened on the device
+                    truth_u8[a:b].copy_(true_host[a:b], non_blocking=True)
+                    truth[a:b].copy_(truth_u8[a:b])
+                else:
+                    truth[a:b].copy_(true_host[a:b], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(side)
                 events.append(ev)
-        keep = []
+        # forward and backward of a group run back to back on this stream, so ONE state buffer (sized for the
+        # largest group) and the cached scratch serve every group
+        state, scratch = _buffers(max(bounds[i + 1] - bounds[i] for i in range(chunks)), C, H, W, feat_d, dev)
         for i in range(chunks):
             a, b = bounds[i], bounds[i + 1]
             cur.wait_event(events[i])
-            ws = _workspace(b - a, C, H, W, feat_d, dev)
-            keep.append(ws)
             rc = L.tl_forward(pred[a:b].data_ptr(), truth[a:b].data_ptr(), b - a, C, H, W, feat_d, float(loss_q),
-                              float(lamda), int(bool(loss_r)), B, ws.data_ptr(), ws.numel(),
-                              parts[i:].data_ptr(), cur.cuda_stream)
+                              float(lamda), int(bool(loss_r)), B, state.data_ptr(), state.numel(),
+                              scratch.data_ptr(), scratch.numel(), parts[i:].data_ptr(), cur.cuda_stream)
             _lib.check(rc, "tl_forward")
             if want_grad:
-                rc = L.tl_backward(None, ws.data_ptr(), ws.numel(), b - a, C, H, W, feat_d, float(loss_q),
+                rc = L.tl_backward(None, state.data_ptr(), state.numel(), b - a, C, H, W, feat_d, float(loss_q),
                                    float(lamda), int(bool(loss_r)), B, grad[a:b].data_ptr(), cur.cuda_stream)
                 _lib.check(rc, "tl_backward")
+        ring.post(state, dev)  # the last group's status; the loss carries a NaN for any group
         loss = parts.sum()
+        for t in (pred, truth, truth_u8, state):  # allocated on this stream, last used here or on the copy stream
+            if t is not None:
+                t.record_stream(side)
+    if grad is not None and orig_shape is not None:
+        grad = grad.reshape(orig_shape)
     return loss, grad
 
 
@@ -334,7 +439,9 @@ def persistence_pairs(maps: torch.Tensor, dim: int) -> List[torch.Tensor]:
         _lib.check(cap, "tl_max_pairs")
     dev = maps.device
     with torch.cuda.device(dev):
-        ws = _workspace(n, 1, H, W, dim, dev)
+        nb = ctypes.c_size_t(0)
+        _lib.check(L.tl_pairs_workspace_bytes(n, H, W, dim, ctypes.byref(nb)), "tl_pairs_workspace_bytes")
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
         pairs = torch.empty((n, cap, 2), dtype=torch.int32, device=dev)
         counts = torch.empty((n,), dtype=torch.int32, device=dev)
         rc = L.tl_persistence_pairs(flat.data_ptr(), n, H, W, dim, ws.data_ptr(), ws.numel(), pairs.data_ptr(),

@@ -15,9 +15,11 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless its comment says host;
- *   - the caller owns every buffer, including the workspace (size from
- *     tl_workspace_bytes); the library never allocates or frees device memory and keeps
- *     no global device state;
+ *   - the caller owns every buffer, including the two workspaces (sizes from
+ *     tl_workspace_bytes): STATE, which tl_forward fills and tl_backward reads, and SCRATCH,
+ *     which is only live inside one call and may be shared by every call enqueued on the same
+ *     stream; the library never allocates or frees device memory and keeps no device state.
+ *     The only host state is process-wide: the options below and the timing aid;
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point
  *     synchronises the host with the device;
  *   - every function returns TL_OK (0) or a negative TL_ERR_* code; tl_last_error()
@@ -44,7 +46,7 @@ extern "C" {
 #define TL_ERR_WORKSPACE (-2) /* workspace too small */
 #define TL_ERR_CUDA (-3)      /* a CUDA runtime call failed; see tl_last_error() */
 
-#define TL_ABI_VERSION 1
+#define TL_ABI_VERSION 2
 
 /* ABI version of the loaded library (TL_ABI_VERSION it was built with). */
 int tl_version(void);
@@ -53,11 +55,40 @@ int tl_version(void);
 const char* tl_last_error(void);
 
 /*
- * Bytes of device workspace needed by tl_forward / tl_backward / tl_persistence_pairs for
- * maps of this shape.  feat_d in {0, 1} is the homology dimension that will be used
- * (batch_iter(..., dim=feat_d), topological_loss.py:68-75).  *bytes is a host pointer.
+ * Process-wide options.  Initial values are read from the environment ONCE, when the library is
+ * loaded (TL_FORCE_GLOBAL, TL_PROFILE, TL_NO_BINARY, TL_WORST_CASE_WORKSPACE = "1"); tl_set_option
+ * changes them afterwards.  FORCE_GLOBAL_KERNEL and WORST_CASE_WORKSPACE change the workspace layout:
+ * use the same setting for tl_workspace_bytes and the calls that consume its sizes.
  */
-int tl_workspace_bytes(int B, int C, int H, int W, int feat_d, size_t* bytes);
+#define TL_OPT_FORCE_GLOBAL_KERNEL 0  /* tests: every shape through the global-memory persistence kernel */
+#define TL_OPT_PROFILE 1              /* accumulate per-phase cycle counters (tl_debug_profile) */
+#define TL_OPT_NO_BINARY_PATH 2       /* measurement: two-valued maps through the generic path */
+#define TL_OPT_WORST_CASE_WORKSPACE 3 /* size every table for the worst case: no input can overflow */
+#define TL_OPT_COUNT_ 4
+int tl_set_option(int which, int value);
+int tl_get_option(int which);
+
+/*
+ * Bytes of device memory tl_forward / tl_backward need for maps of this shape.  feat_d in {0, 1} is
+ * the homology dimension that will be used (batch_iter(..., dim=feat_d), topological_loss.py:68-75).
+ *   *state_bytes    header + per-map bookkeeping + the PAIR ARENA: one pool of (creator, destroyer,
+ *                   birth, death, matched point) records shared by all maps, carved with a device
+ *                   counter.  The returned size holds max(H*W/5 + 64, 8192) pairs per map, both sets together
+ *                   (a noise-like prediction produces ~H*W/5, segmentation ground truth a handful; maps
+ *                   up to 128 x 128 thereby get the combinatorial maximum); any LARGER buffer is used in full.  With TL_OPT_WORST_CASE_WORKSPACE it holds the
+ *                   combinatorial maximum (H*W/2 + 2 per map and set).
+ *   *scratch_bytes  per-CTA tables of the persistence kernels (independent of B).
+ * Both are host pointers.  If a pathological input exhausts the arena (or, on maps of more than
+ * 65536 pixels with the typical-size tables, the basin tables) nothing is written out of bounds: a
+ * status bit is set, the loss becomes NaN and tl_status reports it.
+ */
+int tl_workspace_bytes(int B, int C, int H, int W, int feat_d, size_t* state_bytes, size_t* scratch_bytes);
+
+#define TL_STATUS_ARENA 1     /* pair arena exhausted */
+#define TL_STATUS_BASINS 2    /* basin tables exhausted (multi-band maps, typical-size workspace) */
+#define TL_STATUS_NONFINITE 4 /* a map holds a NaN */
+/* Host copy of the status word of the last tl_forward that used `state` (0 = fine).  Synchronises `stream`. */
+int tl_status(const void* state, int* host_status, void* stream);
 
 /*
  * Forward pass of topo_loss for interp == 0 (topological_loss.py:55-96):
@@ -70,22 +101,23 @@ int tl_workspace_bytes(int B, int C, int H, int W, int feat_d, size_t* bytes);
  *          [+ lamda / (B_global*C) * sum_{b,c} sum_pairs |d-b|^q   if loss_r (:88-94)].
  * B_global is the batch size the mean runs over; pass B (or 0) on one GPU, the global
  * batch when the batch axis is sharded over ranks (the caller then all-reduces loss_out).
- * loss_out: one fp32 on the device.  The workspace keeps what tl_backward needs.
+ * loss_out: one fp32 on the device.  `state` keeps what tl_backward needs.
  */
 int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W,
                int feat_d, float q, float lamda, int loss_r, int B_global,
-               void* ws, size_t ws_bytes, float* loss_out, void* stream);
+               void* state, size_t state_bytes, void* scratch, size_t scratch_bytes,
+               float* loss_out, void* stream);
 
 /*
  * Backward pass (the autograd graph of training_utils.py:66 restricted to this loss):
  * grad_pred[B,C,H,W] = grad_loss * d loss / d pred, fully overwritten (zeros included).
  * grad_loss: one fp32 on the device (upstream gradient), or NULL for 1.0.
- * `ws` must be the workspace a tl_forward call filled; shape, feat_d, q, lamda, loss_r and
+ * `state` must be the buffer a tl_forward call filled; shape, feat_d, q, lamda, loss_r and
  * B_global must be the values given to that call (the library keeps no state between calls).
  * An image whose summed cost S_b is exactly 0 gets NaN on all its critical pixels, as the
  * reference's autograd does (0 * inf through pow(1/q)).
  */
-int tl_backward(const float* grad_loss, const void* ws, size_t ws_bytes,
+int tl_backward(const float* grad_loss, const void* state, size_t state_bytes,
                 int B, int C, int H, int W, int feat_d, float q, float lamda, int loss_r,
                 int B_global, float* grad_pred, void* stream);
 
@@ -96,8 +128,9 @@ int tl_backward(const float* grad_loss, const void* ws, size_t ws_bytes,
  * (creator, destroyer) of homology dimension `dim` into pairs[map][k][2], sorted in
  * gudhi's emission order (filtration order of the death cell; essential H0 class last),
  * and the count into counts[map].  A map with more than `cap` pairs reports its true count
- * and writes only the first `cap`.
+ * and writes only the first `cap`.  `ws`: one buffer of tl_pairs_workspace_bytes bytes.
  */
+int tl_pairs_workspace_bytes(int n_maps, int H, int W, int dim, size_t* bytes);
 int tl_persistence_pairs(const float* maps, int n_maps, int H, int W, int dim,
                          void* ws, size_t ws_bytes,
                          int32_t* pairs, int cap, int32_t* counts, void* stream);
@@ -118,18 +151,19 @@ int tl_wasserstein(const float* D1, const int32_t* off1, const float* D2, const 
 
 /*
  * Debug aid, not on the hot path: host copy of the 8 per-phase cycle counters the persistence
- * kernel accumulates into the workspace when the process environment has TL_PROFILE=1.
+ * kernel accumulates into the state buffer while TL_OPT_PROFILE is set.
  * Synchronises the device.  host_out8: 8 x uint64 on the host.
  */
-int tl_debug_profile(const void* ws, unsigned long long* host_out8);
+int tl_debug_profile(const void* state, unsigned long long* host_out8);
 
 /*
- * Measurement aid for bench.py's roofline: while enabled on the calling thread, tl_forward and
- * tl_backward bracket each of their kernels with cudaEventRecord on the caller's stream (the
- * stream the kernels are launched on).  tl_timing_read synchronises those events and returns, on
- * the host, the summed milliseconds of the 6 stages [persistence, segmented sort, matching, loss,
- * grad zero-fill, grad scatter] over the calls since the last enable/read (at most 128), and the
- * number of forward / backward calls in n_calls[0..1].
+ * Measurement aid for bench.py's roofline: while enabled (process-wide, mutex-guarded: the backward
+ * runs on autograd's thread), tl_forward and tl_backward bracket their kernels with
+ * cudaEventRecord on the caller's stream (the stream the kernels are launched on).
+ * tl_timing_read synchronises those events and returns, on the host, the summed milliseconds of
+ * the 6 stages [persistence, (unused), matching, loss, (unused), gradient fill + scatter] over the
+ * calls since the last enable/read (at most 128), and the number of forward / backward calls in
+ * n_calls[0..1].
  */
 int tl_timing_enable(int on);
 int tl_timing_read(float* ms_sum6, int* n_calls);

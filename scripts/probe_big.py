@@ -21,6 +21,6 @@ for B, HW, dim in ((4, 1024, 1), (16, 1024, 1), (64, 256, 0), (64, 50, 1), (64, 
         p.grad = None
         tlb.topo_loss(p, truth, 0.1, feat_d=dim).backward()
     ms = timeit(f)
-    print(f"B={B} {HW}x{HW} feat_d={dim}: fwd+bwd {ms:.2f} ms -> {B*14/ms*1e3:.0f} maps/s, ws {tlb.topological_loss._workspace(B,14,HW,HW,dim,'cuda').numel()/1e9:.2f} GB", flush=True)
+    print(f"B={B} {HW}x{HW} feat_d={dim}: fwd+bwd {ms:.2f} ms -> {B*14/ms*1e3:.0f} maps/s, ws {sum(t.numel() for t in tlb.topological_loss._buffers(B,14,HW,HW,dim,torch.device('cuda',0)))/1e9:.2f} GB", flush=True)
     del pred, truth, p
     torch.cuda.empty_cache()

@@ -7,7 +7,8 @@ from dilabhelmholtzoct_b200.synthetic import make_batch
 def load(name):
     L = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dilabhelmholtzoct_b200", name))
     vp = ctypes.c_void_p
-    L.tl_workspace_bytes.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_size_t)]
+    L.tl_pairs_workspace_bytes.argtypes = [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_size_t)]
+    L.tl_set_option.argtypes = [ctypes.c_int, ctypes.c_int]
     L.tl_persistence_pairs.argtypes = [vp] + [ctypes.c_int] * 4 + [vp, ctypes.c_size_t, vp, ctypes.c_int, vp, vp]
     L.tl_max_pairs.argtypes = [ctypes.c_int] * 3
     L.tl_debug_profile.argtypes = [vp, vp]
@@ -16,7 +17,7 @@ def load(name):
 def run(L, maps, dim, stats):
     n, H, W = maps.shape
     nb = ctypes.c_size_t(0)
-    L.tl_workspace_bytes(n, 1, H, W, dim, ctypes.byref(nb))
+    L.tl_pairs_workspace_bytes(n, H, W, dim, ctypes.byref(nb))
     ws = torch.empty(nb.value, dtype=torch.uint8, device="cuda")
     cap = L.tl_max_pairs(H, W, dim)
     pairs = torch.empty((n, cap, 2), dtype=torch.int32, device="cuda")
@@ -47,13 +48,13 @@ def run(L, maps, dim, stats):
     return res
 
 if __name__ == '__main__':
-    os.environ["TL_PROFILE"] = "1"
     pred, truth = make_batch(16, 256, 256, seed=1234, device="cuda")
     P = pred.reshape(-1, 256, 256).contiguous(); T = truth.reshape(-1, 256, 256).contiguous()
     X = torch.rand((224, 256, 256), device="cuda")
     S = torch.nn.functional.avg_pool2d(torch.rand((224, 1, 768, 768), device="cuda"), 3).reshape(224, 256, 256).contiguous()
     for name in os.environ.get("TL_PROBE_LIBS", "libtopoloss_stats.so,libtopoloss.so").split(","):
         L = load(name)
+        L.tl_set_option(1, 1)  # TL_OPT_PROFILE
         stats = "stats" in name
         for tag, m in (("pred", P), ("truth", T), ("iid", X), ("smooth3", S)):
             run(L, m, 1, stats)

@@ -17,15 +17,15 @@ def timeit(fn, n=5, warm=2):
 import ctypes
 from dilabhelmholtzoct_b200 import _lib
 def profile(pred, truth, dim):
-    os.environ["TL_PROFILE"] = "1"
+    _lib.lib().tl_set_option(_lib.OPT_PROFILE, 1)
     B, C, H, W = pred.shape
-    ws = tlb.topological_loss._workspace(B, C, H, W, dim, pred.device)
+    ws, sc = tlb.topological_loss._buffers(B, C, H, W, dim, pred.device)
     loss = torch.empty((), device="cuda")
-    _lib.lib().tl_forward(pred.data_ptr(), truth.data_ptr(), B, C, H, W, dim, 2.0, 0.1, 0, 0, ws.data_ptr(), ws.numel(), loss.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.lib().tl_forward(pred.data_ptr(), truth.data_ptr(), B, C, H, W, dim, 2.0, 0.1, 0, 0, ws.data_ptr(), ws.numel(), sc.data_ptr(), sc.numel(), loss.data_ptr(), torch.cuda.current_stream().cuda_stream)
     out = (ctypes.c_ulonglong * 8)()
     _lib.lib().tl_debug_profile.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     _lib.lib().tl_debug_profile(ws.data_ptr(), out)
-    os.environ["TL_PROFILE"] = "0"
+    _lib.lib().tl_set_option(_lib.OPT_PROFILE, 0)
     tot = sum(out) or 1
     return [round(100.0 * v / tot, 1) for v in out], tot
 

@@ -19,7 +19,7 @@ def _declared():
 def test_header_declares_the_expected_entry_points():
     names = _declared()
     for must in ["tl_forward", "tl_backward", "tl_workspace_bytes", "tl_persistence_pairs", "tl_wasserstein",
-                 "tl_last_error", "tl_version"]:
+                 "tl_last_error", "tl_version", "tl_status", "tl_set_option", "tl_pairs_workspace_bytes"]:
         assert must in names
 
 
@@ -34,22 +34,50 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.SIGNATURES) <= set(_declared())
 
 
+def _ws(L, B, C, H, W, d):
+    ns, nc = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    rc = L.tl_workspace_bytes(B, C, H, W, d, ctypes.byref(ns), ctypes.byref(nc))
+    return rc, ns.value, nc.value
+
+
 def test_workspace_bytes_and_argument_errors():
     from dilabhelmholtzoct_b200 import _lib
     L = _lib.lib()
-    n = ctypes.c_size_t(0)
-    assert L.tl_workspace_bytes(64, 14, 256, 256, 1, ctypes.byref(n)) == 0 and n.value > 64 * 14 * 256 * 256
-    small = ctypes.c_size_t(0)
-    assert L.tl_workspace_bytes(2, 14, 50, 50, 1, ctypes.byref(small)) == 0 and small.value < n.value
-    assert L.tl_workspace_bytes(2, 14, 50, 50, 2, ctypes.byref(n)) == -1      # feat_d = 2 is invalid on 2-D maps
+    rc, ns, nc = _ws(L, 64, 14, 256, 256, 1)
+    assert rc == 0 and ns > 0 and nc > 0
+    rc, ns2, nc2 = _ws(L, 2, 14, 50, 50, 1)
+    assert rc == 0 and ns2 < ns and nc2 < nc
+    assert _ws(L, 2, 14, 50, 50, 2)[0] == -1      # feat_d = 2 is invalid on 2-D maps
     assert b"feat_d" in L.tl_last_error()
-    assert L.tl_workspace_bytes(2, 14, 50, 60, 1, ctypes.byref(n)) == -1      # non-square
-    assert L.tl_workspace_bytes(0, 14, 50, 50, 1, ctypes.byref(n)) == -1
+    assert _ws(L, 2, 14, 50, 60, 1)[0] == -1      # non-square
+    assert _ws(L, 0, 14, 50, 50, 1)[0] == -1
     assert L.tl_max_pairs(256, 256, 1) == 256 * 256 // 2 + 2
     with pytest.raises(ValueError):
         _lib.check(-1, "x")
     with pytest.raises(RuntimeError):
         _lib.check(-3, "x")
+
+
+def test_workspace_is_small():
+    """the headline shape needs <= 0.7 GB (was 3.41 GB), BASELINE configs[4]'s per-GPU shard
+    (16 x 14 maps of 1024 x 1024) <= 6 GB (was 30.6 GB); the scratch part does not grow with the batch; the
+    worst-case option restores the combinatorial maximum."""
+    from dilabhelmholtzoct_b200 import _lib
+    L = _lib.lib()
+    assert L.tl_get_option(_lib.OPT_WORST_CASE_WORKSPACE) == 0
+    rc, ns, nc = _ws(L, 64, 14, 256, 256, 1)
+    assert rc == 0 and ns + nc <= 0.7e9, (ns, nc)
+    assert ns >= 64 * 14 * 13000 * 24          # room for ~13 k pairs per map (iid noise: 12.9 k)
+    rc, ns5, nc5 = _ws(L, 16, 14, 1024, 1024, 1)
+    assert rc == 0 and ns5 + nc5 <= 6e9, (ns5, nc5)
+    assert _ws(L, 8, 14, 256, 256, 1)[2] == nc  # scratch is per CTA, not per map
+    try:
+        assert L.tl_set_option(_lib.OPT_WORST_CASE_WORKSPACE, 1) == 0
+        rc, nsw, ncw = _ws(L, 64, 14, 256, 256, 1)
+        assert rc == 0 and nsw >= 64 * 14 * 2 * (256 * 256 // 2 + 2) * 24 and ncw >= nc
+    finally:
+        L.tl_set_option(_lib.OPT_WORST_CASE_WORKSPACE, 0)
+    assert L.tl_set_option(99, 1) == -1
 
 
 def test_product_has_no_cpu_path_and_never_imports_the_oracle():

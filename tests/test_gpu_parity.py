@@ -83,14 +83,22 @@ def test_pairs_banded_maps(dim):
 
 
 @pytest.mark.parametrize("dim", [0, 1])
-def test_pairs_global_memory_kernel(dim, monkeypatch):
+def test_pairs_global_memory_kernel(dim):
     """The global-memory kernel (maps wider than the shared-memory kernel's row limit), forced here."""
-    monkeypatch.setenv("TL_FORCE_GLOBAL", "1")
-    rng = np.random.default_rng(8)
-    maps = rng.random((3, 70, 70)).astype(np.float32)
-    maps[1] = np.round(maps[1] * 4) / 4
-    maps[2] = (maps[2] > 0.5).astype(np.float32)
-    _assert_same_pairs(maps, dim)
+    from dilabhelmholtzoct_b200 import _lib
+    L = _lib.lib()
+    L.tl_set_option(_lib.OPT_FORCE_GLOBAL_KERNEL, 1)
+    try:
+        rng = np.random.default_rng(8)
+        maps = rng.random((3, 70, 70)).astype(np.float32)
+        maps[1] = np.round(maps[1] * 4) / 4
+        maps[2] = (maps[2] > 0.5).astype(np.float32)
+        _assert_same_pairs(maps, dim)
+        from dilabhelmholtzoct_b200.synthetic import make_batch
+        pred, truth = make_batch(2, 40, 40, seed=8, n_classes=3)
+        _check_loss(pred, truth, 0.1, dim)
+    finally:
+        L.tl_set_option(_lib.OPT_FORCE_GLOBAL_KERNEL, 0)
 
 
 def test_pairs_many_basins_table_spills_to_global():
@@ -406,3 +414,108 @@ def test_pairs_repeatable_at_c2_scale():
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
     want = oracle.cubical_pairs(maps[5], 1)
     assert np.array_equal(a[5], want)
+
+
+def test_forward_under_inference_mode():
+    """validate_model calls the loss under torch.inference_mode() (training_utils.py:356-378): same value, no graph."""
+    import dilabhelmholtzoct_b200 as tlb
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(2, 64, 64, seed=41, n_classes=3)
+    want, _, _ = oracle.topo_loss(pred.numpy(), truth.numpy(), 0.1, feat_d=1)
+    with torch.inference_mode():
+        loss = tlb.topo_loss(pred.cuda(), truth.cuda(), 0.1, feat_d=1, interp=0)
+        fused = tlb.topo_loss_from_logits(torch.logit(pred.clamp(1e-4, 1 - 1e-4)).cuda(), truth.cuda(), 0.1, feat_d=1, interp=32)
+    assert not loss.requires_grad and abs(float(loss) - want) <= REL * abs(want)
+    assert torch.isfinite(fused) and not fused.requires_grad
+    with torch.no_grad():
+        assert float(tlb.topo_loss(pred.cuda(), truth.cuda(), 0.1, feat_d=1)) == float(loss)
+
+
+def test_nan_and_inf_pixels():
+    """A NaN pixel (sigmoid of a diverged logit) makes the cell order undefined: the kernels terminate, the loss is
+    NaN and the status word says why; +/-inf are ordinary ordered values."""
+    import dilabhelmholtzoct_b200 as tlb
+    rng = np.random.default_rng(2)
+    f = rng.random((2, 2, 32, 32)).astype(np.float32)
+    g = f.copy(); g[0, 1, 5, 7] = np.inf; g[1, 0, 3, 3] = -np.inf
+    _assert_same_pairs(g.reshape(-1, 32, 32), 1)
+    _assert_same_pairs(g.reshape(-1, 32, 32), 0)
+    bad = f.copy(); bad[1, 1, 9, 9] = np.nan
+    for dim in (0, 1):
+        p = torch.tensor(bad, device="cuda", requires_grad=True)
+        loss = tlb.topo_loss(p, torch.tensor(f, device="cuda"), 0.1, feat_d=dim)
+        assert torch.isnan(loss)
+        with pytest.raises(RuntimeError, match="NaN"):
+            tlb.check_status(sync=True)
+    two = (f > 0.5).astype(np.float32); two[0, 0, 4, 4] = np.nan  # would-be two-valued map with a NaN
+    loss = tlb.topo_loss(torch.tensor(two, device="cuda"), torch.tensor(f, device="cuda"), 0.1, feat_d=1)
+    assert torch.isnan(loss)
+    with pytest.raises(RuntimeError, match="NaN"):
+        tlb.check_status(sync=True)
+    tlb.check_status(sync=True)  # reported once
+
+
+def test_arena_overflow_is_loud():
+    """A state buffer too small for the pairs of the batch: nothing is written out of bounds, the loss is NaN,
+    tl_status / check_status say 'arena', and a larger arena (set_arena_factor) fixes it."""
+    import ctypes
+    import dilabhelmholtzoct_b200 as tlb
+    from dilabhelmholtzoct_b200 import _lib
+    from dilabhelmholtzoct_b200.topological_loss import _buffers
+    L = _lib.lib()
+    rng = np.random.default_rng(4)
+    B, C, S = 2, 3, 64
+    pred = torch.tensor(rng.random((B, C, S, S)).astype(np.float32), device="cuda")
+    truth = (pred > 0.7).float()
+    dev = pred.device
+    state, scratch = _buffers(B, C, S, S, 1, dev)
+    ns, nc = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    L.tl_workspace_bytes(B, C, S, S, 1, ctypes.byref(ns), ctypes.byref(nc))
+    per_map = min(2 * (S * S // 2 + 2), max(S * S // 5 + 64, 8192))  # arena records per map that tl_workspace_bytes asks for
+    tiny = state[: ns.value - (B * C * per_map - 100) * 24]           # room for 100 records only
+    guard = torch.full((4096,), 0x5A, dtype=torch.uint8, device=dev)
+    buf = torch.cat([tiny, guard])
+    loss = torch.zeros((), device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = L.tl_forward(pred.data_ptr(), truth.data_ptr(), B, C, S, S, 1, 2.0, 0.1, 0, 0, buf.data_ptr(), tiny.numel(),
+                      scratch.data_ptr(), scratch.numel(), loss.data_ptr(), st)
+    assert rc == 0
+    status = ctypes.c_int(0)
+    assert L.tl_status(buf.data_ptr(), ctypes.byref(status), st) == 0
+    assert status.value & 1 and torch.isnan(loss)
+    assert bool((buf[tiny.numel():] == 0x5A).all()), "records written past the arena"
+    grad = torch.empty_like(pred)
+    assert L.tl_backward(None, buf.data_ptr(), tiny.numel(), B, C, S, S, 1, 2.0, 0.1, 0, 0, grad.data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    full = tlb.topo_loss(pred, truth, 0.1, feat_d=1)
+    assert torch.isfinite(full)
+    tlb.check_status(sync=True)
+
+
+def test_host_api_uint8_truth_and_batch_of_one():
+    import dilabhelmholtzoct_b200 as tlb
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(5, 64, 64, seed=32, n_classes=3)
+    want_loss, want_grad = _loss_and_grad(pred, truth, 0.1, feat_d=1)
+    loss, grad = tlb.topo_loss_from_host(pred.pin_memory(), truth.to(torch.uint8).pin_memory(), 0.1, feat_d=1, chunks=3)
+    assert abs(float(loss) - want_loss) <= REL * abs(want_loss)
+    assert np.abs(grad.cpu().numpy() - want_grad).max() <= REL * np.abs(want_grad).max()
+    p1, t1 = pred[:1].contiguous(), truth[:1].contiguous()
+    w1, g1 = _loss_and_grad(p1, t1, 0.1, feat_d=1)
+    loss1, grad1 = tlb.topo_loss_from_host(p1.pin_memory(), t1.pin_memory(), 0.1, feat_d=1)
+    assert tuple(grad1.shape) == tuple(p1.shape) and abs(float(loss1) - w1) <= REL * abs(w1)
+    assert np.abs(grad1.cpu().numpy() - g1).max() <= REL * np.abs(g1).max()
+    with pytest.raises(ValueError, match="pinned"):
+        tlb.topo_loss_from_host(pred, truth, 0.1, feat_d=1)
+    with pytest.raises(ValueError, match="HOST"):
+        tlb.topo_loss_from_host(pred.cuda(), truth.cuda(), 0.1, feat_d=1)
+
+
+def test_double_backward_raises():
+    import dilabhelmholtzoct_b200 as tlb
+    p = torch.rand((2, 2, 16, 16), device="cuda", requires_grad=True)
+    t = (torch.rand((2, 2, 16, 16), device="cuda") > 0.5).float()
+    loss = tlb.topo_loss(p, t, 0.1, feat_d=1)
+    (g,) = torch.autograd.grad(loss, p, create_graph=True)
+    with pytest.raises(RuntimeError):
+        g.sum().backward()
