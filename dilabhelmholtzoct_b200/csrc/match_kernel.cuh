@@ -202,7 +202,10 @@ struct MatchFwdArgs {
     unsigned int* counter;
 };
 
+constexpr int kColCache = 12288;  // columns (b, d) kept in dynamic shared memory: 96 KB
+
 __global__ void __launch_bounds__(kMatchThreads) match_small_kernel(MatchFwdArgs A) {
+    extern __shared__ __align__(8) float2 s_col[];  // [kColCache] points of the larger diagram
     __shared__ double s_red[kMatchThreads / 32];
     __shared__ double s_bv[kMatchThreads / 32];
     __shared__ int s_bk[kMatchThreads / 32], s_bw[kMatchThreads / 32];
@@ -246,6 +249,10 @@ __global__ void __launch_bounds__(kMatchThreads) match_small_kernel(MatchFwdArgs
         }
         if (tid <= R) s_u[tid] = 0.0;
         if (tid == 0) s_nT = 0;
+        // the columns are read once per step of every phase: keep them on chip (a step is then a shared-memory
+        // sweep instead of a round trip to L2)
+        const bool cached = Cn <= kColCache;
+        if (cached) for (int c = tid; c < Cn; c += nt) s_col[c] = make_float2(rC[c].b, rC[c].d);
         __syncthreads();
         for (int r = 1; r <= R; ++r) {
             if (tid == 0) { s_nU = 1; s_Ucol[0] = 0; s_Urow[0] = r; }
@@ -261,7 +268,10 @@ __global__ void __launch_bounds__(kMatchThreads) match_small_kernel(MatchFwdArgs
                     for (int t = 0; t < nT; ++t) if (s_tc[t] == c) vc = s_tv[t];
                     float cb = 0.f, cd = 0.f; double cdg = 0.0;
                     const bool real = c <= Cn;
-                    if (real) { cb = rC[c - 1].b; cd = rC[c - 1].d; cdg = (double)cost_diag(cb, cd, q); }
+                    if (real) {
+                        if (cached) { const float2 p = s_col[c - 1]; cb = p.x; cd = p.y; } else { cb = rC[c - 1].b; cd = rC[c - 1].d; }
+                        cdg = (double)cost_diag(cb, cd, q);
+                    }
                     double mv = kInf; int way = 0;
                     for (int t = 0; t < nU; ++t) {  // tree rows in the order they joined: the first strict minimum wins
                         const int i = s_Urow[t] - 1;
@@ -375,7 +385,7 @@ struct GradArgs {
 // One CTA per map: zero-fill the map's gradient (128-bit stores, the lines stay in L2), then scatter-add
 // the pairs into the critical pixels.  Fusing the fill keeps the atomics off cold DRAM lines and saves the
 // separate memset pass.
-__global__ void __launch_bounds__(512) grad_kernel(GradArgs A) {
+__global__ void __launch_bounds__(256) grad_kernel(GradArgs A) {
     const double gl = A.grad_loss ? (double)__ldg(A.grad_loss) : 1.0;
     const double q = (double)A.q;
     for (int map = blockIdx.x; map < A.M; map += gridDim.x) {

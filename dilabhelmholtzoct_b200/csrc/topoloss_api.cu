@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "dice_ce_kernel.cuh"
 #include "match_kernel.cuh"
 #include "ph_kernel.cuh"
 #include "ph_small.cuh"
@@ -395,7 +396,8 @@ int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W
     mf.cost = at<double>(state, S.cost); mf.tpers = at<double>(state, S.tpers);
     mf.heavy = at<int32_t>(state, S.heavy); mf.n_heavy = at<unsigned int>(state, 20);
     mf.counter = at<unsigned int>(state, 24);
-    tl::match_small_kernel<<<M < kMatchSlots ? M : kMatchSlots, tl::kMatchThreads, 0, st>>>(mf);
+    TL_CUDA(cudaFuncSetAttribute(tl::match_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tl::kColCache * 8));
+    tl::match_small_kernel<<<M < kMatchSlots ? M : kMatchSlots, tl::kMatchThreads, tl::kColCache * 8, st>>>(mf);
     TL_CUDA(cudaGetLastError());
     {   // maps with two large diagrams (none for segmentation ground truth): general kernel, global scratch
         tl::MatchArgs m;
@@ -441,7 +443,7 @@ int tl_backward(const float* grad_loss, const void* state, size_t state_bytes, i
     g.coef = at<double>(w, S.coef); g.grad_loss = grad_loss;
     g.M = M; g.C = C; g.N = H * W; g.B_global = B_global; g.loss_r = loss_r;
     g.q = q; g.lamda = lamda; g.grad_pred = grad_pred;
-    tl::grad_kernel<<<M < 1184 ? M : 1184, 512, 0, st>>>(g);
+    tl::grad_kernel<<<M < 1184 ? M : 1184, 256, 0, st>>>(g);  // 8 CTAs per SM: 1184 maps in flight, C2's 896 in one wave
     TL_CUDA(cudaGetLastError());
     tm.mark(7, st);
     return TL_OK;
@@ -654,6 +656,60 @@ int tl_postprocess_backward(const float* grad_out, int n_maps, int Hs, int Ws, i
     const long long n_tiles = (long long)n_maps * tiles_y * tiles_x;
     const long long cap = 148ll * 32;
     tl::postprocess_bwd_kernel<<<(int)(n_tiles < cap ? n_tiles : cap), 256, 0, st>>>(a, tiles_y, tiles_x);
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+namespace {
+int dice_ce_args(tl::DiceCeArgs& a, const float* x, const float* t, int B, int C, int HW, void* ws) {
+    if (!x || !t || !ws) return fail(TL_ERR_ARG, "null pointer");
+    if (B <= 0 || C <= 0 || HW <= 0) return fail(TL_ERR_ARG, "bad shape [%d,%d,%d]", B, C, HW);
+    if (C > tl::kDcMaxC) return fail(TL_ERR_ARG, "at most %d channels (got %d)", tl::kDcMaxC, C);
+    if ((long long)B * C * HW >= (1ll << 40)) return fail(TL_ERR_ARG, "too large");
+    a.x = x; a.t = t; a.B = B; a.C = C; a.HW = HW;
+    a.tiles = (HW + tl::kDcThreads * tl::kDcPix - 1) / (tl::kDcThreads * tl::kDcPix);
+    a.acc = static_cast<double*>(ws); a.loss_out = nullptr; a.grad_loss = nullptr; a.gx = nullptr;
+    return TL_OK;
+}
+int dice_ce_grid(const tl::DiceCeArgs& a) {
+    const long long jobs = (long long)a.B * a.tiles, cap = 148ll * 8;
+    return (int)(jobs < cap ? jobs : cap);
+}
+}  // namespace
+
+int tl_dice_ce_workspace_bytes(int B, int C, size_t* bytes) {
+    if (!bytes || B <= 0 || C <= 0) return fail(TL_ERR_ARG, "bad arguments");
+    *bytes = sizeof(double) * ((size_t)B * C * 3 + 1);
+    return TL_OK;
+}
+
+int tl_dice_ce_forward(const float* logits, const float* target, int B, int C, int HW, void* ws, float* loss_out, void* stream) {
+    tl::DiceCeArgs a;
+    int rc = dice_ce_args(a, logits, target, B, C, HW, ws);
+    if (rc != TL_OK) return rc;
+    if (!loss_out) return fail(TL_ERR_ARG, "null pointer");
+    a.loss_out = loss_out;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TL_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * ((size_t)B * C * 3 + 1), st));
+    tl::dice_ce_fwd_kernel<<<dice_ce_grid(a), tl::kDcThreads, 0, st>>>(a);
+    TL_CUDA(cudaGetLastError());
+    tl::dice_ce_finish_kernel<<<1, 256, 0, st>>>(a);
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+int tl_dice_ce_backward(const float* grad_loss, const float* logits, const float* target, int B, int C, int HW,
+                        const void* ws, float* grad_logits, void* stream) {
+    tl::DiceCeArgs a;
+    int rc = dice_ce_args(a, logits, target, B, C, HW, const_cast<void*>(ws));
+    if (rc != TL_OK) return rc;
+    if (!grad_logits) return fail(TL_ERR_ARG, "null pointer");
+    a.grad_loss = grad_loss; a.gx = grad_logits;
+    tl::dice_ce_bwd_kernel<<<dice_ce_grid(a), tl::kDcThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
     TL_CUDA(cudaGetLastError());
     return TL_OK;
 }

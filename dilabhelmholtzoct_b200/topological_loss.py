@@ -294,6 +294,60 @@ def postprocess_masks(pred_masks: torch.Tensor, reshaped_input_size, original_si
     return _PostprocessFn.apply(pred_masks.contiguous(), int(padded_size), rh, rw, oh, ow)
 
 
+class _DiceCeFn(torch.autograd.Function):
+    """tl_dice_ce_forward / tl_dice_ce_backward."""
+
+    @staticmethod
+    def forward(ctx, x, t):
+        B, C = int(x.shape[0]), int(x.shape[1])
+        HW = 1
+        for d in x.shape[2:]:
+            HW *= int(d)
+        dev = x.device
+        L = _lib.lib()
+        nb = ctypes.c_size_t(0)
+        _lib.check(L.tl_dice_ce_workspace_bytes(B, C, ctypes.byref(nb)), "tl_dice_ce_workspace_bytes")
+        with torch.cuda.device(dev):
+            ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            rc = L.tl_dice_ce_forward(x.data_ptr(), t.data_ptr(), B, C, HW, ws.data_ptr(), loss.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "tl_dice_ce_forward")
+        ctx.save_for_backward(x, t, ws)
+        ctx.meta = (B, C, HW)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, t, ws = ctx.saved_tensors
+        B, C, HW = ctx.meta
+        dev = x.device
+        with torch.cuda.device(dev):
+            g = g.to(device=dev, dtype=torch.float32).contiguous()
+            gx = torch.empty_like(x)
+            rc = _lib.lib().tl_dice_ce_backward(g.data_ptr(), x.data_ptr(), t.data_ptr(), B, C, HW, ws.data_ptr(),
+                                                gx.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "tl_dice_ce_backward")
+        return gx, None
+
+
+def dice_ce_loss(masks: torch.Tensor, gt_masks: torch.Tensor) -> torch.Tensor:
+    """``monai.losses.DiceCELoss(sigmoid=True)(masks, gt_masks)`` -- the reference's ``seg_loss``
+    (training_utils.py:32, :62; monai 1.3.0 defaults: Dice with ``smooth_nr = smooth_dr = 1e-5`` averaged over
+    (b, c), plus ``CrossEntropyLoss`` over the channel axis with the masks as class probabilities) -- as one
+    fused reduction: the two ``[B, C, H, W]`` tensors are read once in the forward and once in the backward.
+    ``masks`` are the decoder's logits (float32, CUDA); the gradient flows to ``masks`` only."""
+    if not (torch.is_tensor(masks) and torch.is_tensor(gt_masks)):
+        raise TypeError("masks and gt_masks must be tensors")
+    if masks.shape != gt_masks.shape or masks.dim() < 3:
+        raise ValueError("expected two [B, C, ...] tensors of the same shape")
+    if not masks.is_cuda or not gt_masks.is_cuda:
+        raise ValueError("dice_ce_loss runs on a CUDA device only: there is no CPU fallback")
+    if masks.dtype != torch.float32:
+        raise ValueError("dice_ce_loss expects float32 logits")
+    return _DiceCeFn.apply(masks.contiguous(), gt_masks.detach().to(torch.float32).contiguous())
+
+
 def topo_loss_from_logits(masks, gt_masks, lamda, interp=0, feat_d=2, loss_q=2, loss_r=False):
     """The reference call site as ONE call (training_utils.py:64 / :375)::
 

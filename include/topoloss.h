@@ -204,6 +204,22 @@ int tl_postprocess_forward(const float* in, int n_maps, int Hs, int Ws, int T, i
 int tl_postprocess_backward(const float* grad_out, int n_maps, int Hs, int Ws, int T, int rh, int rw,
                             int oh, int ow, float* grad_in, void* stream);
 
+/*
+ * F2: the sibling loss of the reference training step,
+ *   seg_loss = monai.losses.DiceCELoss(sigmoid=True)     /root/reference/octsam/models/training_utils.py:32
+ *   train_loss = seg_loss(masks, gt_masks)               training_utils.py:62
+ * (monai 1.3.0, environment.yml:224: mean over (b, c) of 1 - (2 sum s t + 1e-5) / (sum s + sum t + 1e-5) with
+ * s = sigmoid(logits), plus torch.nn.CrossEntropyLoss over the channel axis with the targets as class
+ * probabilities) as one read of the two [B][C][HW] fp32 tensors per pass.  `ws`: tl_dice_ce_workspace_bytes
+ * bytes, filled by the forward and read by the backward; loss_out: one fp32 on the device; grad_loss: one
+ * fp32 on the device or NULL for 1.0; grad_logits [B][C][HW] is fully overwritten.  At most 64 channels.
+ */
+int tl_dice_ce_workspace_bytes(int B, int C, size_t* bytes);
+int tl_dice_ce_forward(const float* logits, const float* target, int B, int C, int HW, void* ws,
+                       float* loss_out, void* stream);
+int tl_dice_ce_backward(const float* grad_loss, const float* logits, const float* target, int B, int C, int HW,
+                        const void* ws, float* grad_logits, void* stream);
+
 /* Bytes of workspace tl_wasserstein needs. */
 int tl_wasserstein_workspace_bytes(int n_diag, int max_rows1, int max_rows2, size_t* bytes);
 

@@ -2,5 +2,5 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 grep -v Warning gpurun_out/pytest_gpu.log | tail -25
-timeout 200 python scripts/r2_probe.py > gpurun_out/r2_probe.log 2>&1; cat gpurun_out/r2_probe.log | cut -c1-400
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 300 python bench.py --config c5 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "bench c5 rc=$?"; cat gpurun_out/bench_c5.json; tail -3 gpurun_out/bench_c5.err

@@ -71,6 +71,58 @@ def test_sharded_loss_equals_unsharded():
         assert abs(wg - float((wgrad * pred.numpy()).sum())) <= 1e-5 * abs(wg)  # all-reduced parameter gradient
 
 
+class _Scale(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.tensor([1.0, 0.5, 2.0]).view(1, 3, 1, 1))
+
+    def forward(self, x):
+        return x * self.w
+
+
+def _ddp_worker(rank, world, port, pred, truth, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from dilabhelmholtzoct_b200.parallel import reduce_scalar_async, shard_batch, topo_loss_sharded
+    sl = shard_batch(pred.shape[0], rank, world)
+    model = DDP(_Scale())
+    # DDP AVERAGES the gradients: the sharded loss must be told (grad_reduce="mean"), otherwise the topological
+    # term would be scaled by 1 / world
+    loss = topo_loss_sharded(model(pred[sl]), truth[sl], 0.1, feat_d=1, global_batch=pred.shape[0], grad_reduce="mean",
+                             loss_fn=_oracle_fn)
+    loss.backward()
+    g_mean = model.module.w.grad.clone()
+    # the share-of-the-global-loss form: no collective inside, the scalar is summed asynchronously
+    model.zero_grad()
+    part = topo_loss_sharded(model(pred[sl]), truth[sl], 0.1, feat_d=1, global_batch=pred.shape[0], grad_reduce="mean",
+                             reduce="local", loss_fn=_oracle_fn)
+    handle = reduce_scalar_async(part)
+    part.backward()
+    out[rank] = (float(loss), g_mean.numpy().copy(), float(handle.result()), model.module.w.grad.numpy().copy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_ddp_with_mean_reduction_equals_single_process():
+    rng = np.random.default_rng(5)
+    pred = torch.tensor(rng.random((4, 3, 14, 14)).astype(np.float32))
+    truth = torch.tensor((rng.random((4, 3, 14, 14)) < 0.4).astype(np.float32))
+    single = _Scale()
+    want = _oracle_fn(single(pred), truth, 0.1, 1, 2, False, 4)
+    want.backward()
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_ddp_worker, args=(world, _free_port(), pred, truth, out), nprocs=world, join=True)
+    for r in range(world):
+        loss, g_mean, loss_async, g_local = out[r]
+        assert abs(loss - float(want)) <= 1e-6 * abs(float(want))
+        assert abs(loss_async - float(want)) <= 1e-6 * abs(float(want))
+        assert np.allclose(g_mean, single.w.grad.numpy(), rtol=1e-5, atol=1e-8)   # DDP's average == single-process gradient
+        assert np.allclose(g_local, single.w.grad.numpy(), rtol=1e-5, atol=1e-8)
+
+
 def test_shard_batch_covers_the_batch():
     from dilabhelmholtzoct_b200.parallel import shard_batch
     for n in (1, 5, 8, 64):

@@ -128,3 +128,41 @@ def test_training_step_on_gpu_uses_the_cuda_op_and_matches_the_oracle_on_the_sam
     after = list(gpu.mask_decoder.parameters())
     assert any(not torch.equal(a, b) for a, b in zip(after, before))  # the decoder was updated
     assert all(p.grad is None for n, p in gpu.named_parameters() if n.startswith("vision_encoder"))
+
+
+def _torch_ops_step(model, inputs, gt, optimizer):
+    """training_utils.py:55-68 on the GPU with PyTorch ops around the CUDA topological loss."""
+    import dilabhelmholtzoct_b200 as tlb
+    from oracle.dice_ce_oracle import dice_ce
+    optimizer.zero_grad()
+    outputs = model(pixel_values=inputs["pixel_values"], input_boxes=inputs["input_boxes"], multimask_output=False)
+    masks = F.interpolate(outputs.pred_masks.squeeze(2), (1024, 1024), mode="bilinear", align_corners=False)
+    masks = masks[..., : inputs["reshaped_input_sizes"][0, 0], : inputs["reshaped_input_sizes"][0, 1]]
+    masks = F.interpolate(masks, (int(inputs["original_sizes"][0, 0]), int(inputs["original_sizes"][0, 1])), mode="bilinear", align_corners=False)
+    loss = dice_ce(masks, gt) + tlb.topo_loss(torch.sigmoid(masks.float()), gt.float(), 0.1, feat_d=1, interp=50)
+    loss.backward()
+    optimizer.step()
+    return loss.detach()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_fused_training_step_equals_the_pytorch_ops_step_on_gpu():
+    """parallel.training_step with this package's kernels for every line around the model (postprocess_masks,
+    dice_ce_loss, fused sigmoid + down-sample + topological loss) against the same step written with PyTorch ops."""
+    from dilabhelmholtzoct_b200.parallel import training_step
+    inputs, gt = _batch(size=96)
+    a = _tiny_sam().cuda()
+    b = copy.deepcopy(a)
+    before = [p.detach().clone() for p in a.mask_decoder.parameters()]
+    ginputs = {k: v.cuda() for k, v in _model_inputs(inputs).items()}
+    stats = {}
+    got = training_step(_SamWithSizes(a), ginputs, gt.cuda(), torch.optim.SGD(a.mask_decoder.parameters(), lr=0.1),
+                        decoder_params=a.mask_decoder.parameters(), stats=stats)
+    want = _torch_ops_step(b, ginputs, gt.cuda(), torch.optim.SGD(b.mask_decoder.parameters(), lr=0.1))
+    assert abs(float(got) - float(want)) <= 1e-4 * abs(float(want)), (float(got), float(want))
+    num = den = 0.0
+    for p0, pa, pb in zip(before, a.mask_decoder.parameters(), b.mask_decoder.parameters()):
+        num += float(((pa - p0) - (pb - p0)).double().pow(2).sum()); den += float((pb - p0).double().pow(2).sum())
+    assert den > 0 and (num / den) ** 0.5 <= 2e-3, (num, den)   # the SGD updates (= gradients) agree
+    assert stats["grad_allreduce_bytes"] == 0                    # single process: nothing to reduce
