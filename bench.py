@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 C = 14
 LAMDA, FEAT_D, LOSS_Q = 0.1, 1, 2
 ALGO_BYTES_PER_PIXEL = 12  # read pred fp32 + read truth fp32 + write grad fp32
-E2E_CHUNKS = 8  # groups of whole images whose H2D copy overlaps the previous group's kernels
+E2E_CHUNKS = 16  # upper bound on the groups of whole images whose H2D copy overlaps the previous group's kernels
 # BASELINE.json configs: c2 = configs[1], the headline (256^2 x 14, bs 64 per GPU); c5 = configs[4], the
 # full-resolution stress test (1024^2 x 14, bs 128 over 8 GPUs = 16 images per GPU)
 CONFIGS = {"c2": dict(side=256, batch=64, seed=2, name="C2"), "c5": dict(side=1024, batch=16, seed=5, name="C5")}

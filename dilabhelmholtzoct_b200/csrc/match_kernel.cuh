@@ -385,7 +385,7 @@ struct GradArgs {
 // One CTA per map: zero-fill the map's gradient (128-bit stores, the lines stay in L2), then scatter-add
 // the pairs into the critical pixels.  Fusing the fill keeps the atomics off cold DRAM lines and saves the
 // separate memset pass.
-__global__ void __launch_bounds__(256) grad_kernel(GradArgs A) {
+__global__ void __launch_bounds__(512) grad_kernel(GradArgs A) {
     const double gl = A.grad_loss ? (double)__ldg(A.grad_loss) : 1.0;
     const double q = (double)A.q;
     for (int map = blockIdx.x; map < A.M; map += gridDim.x) {

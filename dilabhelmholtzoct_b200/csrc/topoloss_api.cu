@@ -443,7 +443,7 @@ int tl_backward(const float* grad_loss, const void* state, size_t state_bytes, i
     g.coef = at<double>(w, S.coef); g.grad_loss = grad_loss;
     g.M = M; g.C = C; g.N = H * W; g.B_global = B_global; g.loss_r = loss_r;
     g.q = q; g.lamda = lamda; g.grad_pred = grad_pred;
-    tl::grad_kernel<<<M < 1184 ? M : 1184, 256, 0, st>>>(g);  // 8 CTAs per SM: 1184 maps in flight, C2's 896 in one wave
+    tl::grad_kernel<<<M < 1184 ? M : 1184, 512, 0, st>>>(g);
     TL_CUDA(cudaGetLastError());
     tm.mark(7, st);
     return TL_OK;

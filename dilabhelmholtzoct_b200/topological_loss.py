@@ -389,7 +389,8 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
     masks are {0, 1} (the reference builds them on the CPU, training_utils.py:413, :432), so they can cross
     PCIe as bytes and be widened on the device (5 instead of 8 bytes per pixel and step).
 
-    The batch is cut into ``chunks`` groups of whole images; group i+1 is copied on a side stream
+    The batch is cut into at most ``chunks`` groups of whole images (one wave of the persistence kernel each when
+    ``chunks`` allows it); group i+1 is copied on a side stream
     while group i runs ``tl_forward`` / ``tl_backward`` (with ``B_global = B`` so the partial losses
     add up to ``lamda * mean_b W_b`` and gradients carry ``1/B``).  Returns ``(loss, grad_pred)``:
     a 0-d device tensor and the ``[B, C, H, W]`` device gradient of the (resampled, if ``interp``)
@@ -423,7 +424,16 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
         pred_host, true_host = pred_host.reshape(C, 1, H, W), true_host.reshape(C, 1, H, W)
         B, C = C, 1
     L = _lib.lib()
+    # The persistence kernel runs one prediction map per SM at a time, so a group of `sms // C` images is one
+    # full wave: finer groups would only add partly filled waves.  `chunks` caps the number of groups.
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    per = max(1, sms // C)
     chunks = max(1, min(int(chunks), B))
+    if chunks >= (B + per - 1) // per:
+        bounds = list(range(0, B, per)) + [B]
+    else:
+        bounds = [(i * B) // chunks for i in range(chunks + 1)]
+    chunks = len(bounds) - 1
     ring = _status_ring(dev)
     ring.poll()
     with torch.cuda.device(dev):
@@ -437,17 +447,12 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
         truth_u8 = torch.empty((B, C, H, W), dtype=torch.uint8, device=dev) if true_host.dtype == torch.uint8 else None
         grad = torch.empty((B, C, H, W), dtype=torch.float32, device=dev) if want_grad else None
         parts = torch.empty((chunks,), dtype=torch.float32, device=dev)
-        bounds = [(i * B) // chunks for i in range(chunks + 1)]
         events = []
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side):  # nothing but copies on this stream: PCIe stays busy back to back
             for i in range(chunks):
                 a, b = bounds[i], bounds[i + 1]
                 pred[a:b].copy_(pred_host[a:b], non_blocking=True)
-                if truth_u8 is not None:  # {0, 1} masks travel as bytes and are widened on the device
-                    truth_u8[a:b].copy_(true_host[a:b], non_blocking=True)
-                    truth[a:b].copy_(truth_u8[a:b])
-                else:
-                    truth[a:b].copy_(true_host[a:b], non_blocking=True)
+                (truth_u8 if truth_u8 is not None else truth)[a:b].copy_(true_host[a:b], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(side)
                 events.append(ev)
@@ -457,6 +462,8 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
         for i in range(chunks):
             a, b = bounds[i], bounds[i + 1]
             cur.wait_event(events[i])
+            if truth_u8 is not None:  # {0, 1} masks travelled as bytes: widen them on the device
+                truth[a:b].copy_(truth_u8[a:b])
             rc = L.tl_forward(pred[a:b].data_ptr(), truth[a:b].data_ptr(), b - a, C, H, W, feat_d, float(loss_q),
                               float(lamda), int(bool(loss_r)), B, state.data_ptr(), state.numel(),
                               scratch.data_ptr(), scratch.numel(), parts[i:].data_ptr(), cur.cuda_stream)

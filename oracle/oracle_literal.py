@@ -23,6 +23,22 @@ published algorithm of those libraries:
   class is paired with ``argmax(x)``; diagram values are re-gathered from ``x``.
 
 It is O(cells^2)-ish and meant for maps up to ~32x32.
+
+KNOWN RISK, H0 ONLY (unverifiable here): the persistence pairing of a TOTAL order is unique, and
+for H1 gudhi derives it from that order through its general cohomology reduction -- which is what this file
+computes.  For dimension 0, however, gudhi's ``Persistent_cohomology::update_cohomology_groups_edge`` takes a
+union-find short cut and decides which of two merging components dies by comparing the FILTRATION VALUES of
+their creators only (``filtration(idx_coc_u) < filtration(idx_coc_v)`` kills v's class, anything else --
+including a tie -- kills u's, u being the first boundary vertex of the merging edge, i.e. the one with the
+smaller bitmap position) [UPSTREAM-RECALL].  When the minima of the two components are exactly equal the
+diagram VALUES are the same under both rules, but the CREATOR PIXEL of the pair (hence where the gradient
+lands) can differ from the canonical (value, dim, position) pairing implemented here, in the fast oracle and
+in the CUDA kernels.  The same short cut also runs for zero-persistence merges, so with tied PIXEL values the
+surviving creator -- and with it the pixel of the essential class -- can move to another pixel of the same
+value (all-zero backgrounds of binary maps).  ``h0_pairs_gudhi_union_find`` below restates that short cut so that the two candidates
+can be told apart the day gudhi is importable (``tests/kats.py::TIE_KATS`` holds an image on which they
+differ; ``tests/golden/make_golden_reference.py`` records what the real library does).  H1 -- the dimension
+the reference call site uses (feat_d=1, training_utils.py:64) -- is not affected.
 """
 from __future__ import annotations
 
@@ -133,3 +149,50 @@ def cubical_pairs_literal(f: np.ndarray):
     pe = _pixel_of(_top_cell(ess[0], val, GH, GW), GW, W)
     amax = int(np.argmax(f))  # first max in raster order (torch.argmax on CPU)
     return h0, h1, (pe, amax)
+
+
+def h0_pairs_gudhi_union_find(f: np.ndarray):
+    """H0 pairs under gudhi's union-find short cut for edges as recalled in the module docstring
+    [UPSTREAM-RECALL]: vertices create classes in filtration order; an edge joining two classes kills the class
+    whose creator has the LARGER filtration value, and on a tie the class of the edge's first boundary vertex
+    (smaller bitmap position).  Returns ``(h0_regular, h0_essential)`` in the format of
+    ``cubical_pairs_literal``.  Differs from the canonical pairing only when two merging components have exactly
+    equal minima."""
+    f = np.asarray(f)
+    H, W = f.shape
+    val, GH, GW = _cells(f)
+    vflat = val.ravel()
+    ncell = GH * GW
+    Ys, Xs = np.divmod(np.arange(ncell), GW)
+    dims = (Ys % 2) + (Xs % 2)
+    order = sorted(range(ncell), key=lambda p: (vflat[p], dims[p], p))
+    parent, creator = {}, {}
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+    h0 = []
+    for p in order:
+        if dims[p] == 0:
+            parent[p] = p
+            creator[p] = p
+        elif dims[p] == 1:
+            Y, X = divmod(p, GW)
+            u, v = (p - 1, p + 1) if X & 1 else (p - GW, p + GW)
+            ru, rv = find(u), find(v)
+            if ru == rv:
+                continue
+            cu, cv = creator[ru], creator[rv]
+            if vflat[cu] < vflat[cv]:
+                dead, live_c = cv, cu
+            else:
+                dead, live_c = cu, cv
+            parent[ru] = rv
+            creator[rv] = live_c
+            if vflat[p] > vflat[dead]:
+                h0.append((_pixel_of(_top_cell(dead, val, GH, GW), GW, W), _pixel_of(_top_cell(p, val, GH, GW), GW, W)))
+    root = find(order[0])
+    ess = (_pixel_of(_top_cell(creator[root], val, GH, GW), GW, W), int(np.argmax(f)))
+    return h0, ess

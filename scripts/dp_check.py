@@ -21,8 +21,9 @@ m = copy.deepcopy(base)
 opt = torch.optim.SGD(m.mask_decoder.parameters(), lr=0.1)
 sl = shard_batch(B, rank, world)
 loc = {k: v[sl].cuda() for k, v in _model_inputs(inputs).items()}
-loss_dp = training_step(_SamWithSizes(m), loc, gt[sl].cuda(), opt, _seg_loss, global_batch=B,
-                        decoder_params=m.mask_decoder.parameters())
+stats = {}
+loss_dp = training_step(_SamWithSizes(m), loc, gt[sl].cuda(), opt, None, global_batch=B,
+                        decoder_params=m.mask_decoder.parameters(), stats=stats)
 # single-process step on the full batch (no process group used: world forced to 1 by a fresh wrapper call)
 m1 = copy.deepcopy(base)
 opt1 = torch.optim.SGD(m1.mask_decoder.parameters(), lr=0.1)
@@ -30,14 +31,48 @@ full = {k: v.cuda() for k, v in _model_inputs(inputs).items()}
 import dilabhelmholtzoct_b200.parallel as par
 _w = par._world
 par._world = lambda group: 1
-loss_1 = training_step(_SamWithSizes(m1), full, gt.cuda(), opt1, _seg_loss, global_batch=B,
+loss_1 = training_step(_SamWithSizes(m1), full, gt.cuda(), opt1, None, global_batch=B,
                        decoder_params=m1.mask_decoder.parameters())
 par._world = _w
 num = den = 0.0
 for a, b, c in zip(m.mask_decoder.parameters(), m1.mask_decoder.parameters(), base.mask_decoder.parameters()):
     num += float(((a - c) - (b - c)).pow(2).sum()); den += float((b - c).pow(2).sum())
+# timing of the data-parallel step at the C3 per-GPU batch (32 images x 14 prompts, 496x512 originals) with the
+# real-size mask decoder (4 058 340 parameters = 16.2 MB of fp32 gradients per all-reduce)
+def _time(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record(); dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / n], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+Bl, Nmax = int(os.environ.get("DP_LOCAL_BATCH", "8")), 14
+g = torch.Generator().manual_seed(100 + rank)
+big = {"pixel_values": torch.randn((Bl, 3, 1024, 1024), generator=g).cuda(),
+       "input_boxes": (torch.rand((Bl, Nmax, 4), generator=g) * 500 + torch.tensor([0.0, 0, 400, 400])).cuda(),
+       "reshaped_input_sizes": torch.tensor([[992, 1024]] * Bl).cuda(), "original_sizes": torch.tensor([[496, 512]] * Bl).cuda()}
+gt_big = (torch.rand((Bl, Nmax, 496, 512), generator=g) < 0.3).float().cuda()
+mt = copy.deepcopy(base)
+optt = torch.optim.Adam(mt.mask_decoder.parameters(), lr=1e-3)
+dec = list(mt.mask_decoder.parameters())
+st2 = {}
+ms_step = _time(lambda: training_step(_SamWithSizes(mt), big, gt_big, optt, None, global_batch=Bl * world, decoder_params=dec, stats=st2))
+from dilabhelmholtzoct_b200.parallel import allreduce_gradients
+ms_ar = _time(lambda: allreduce_gradients(dec), n=20, warm=3)
 out = {"rank": rank, "world": world, "loss_dp": float(loss_dp), "loss_single": float(loss_1),
-       "rel_update_err": (num / max(den, 1e-30)) ** 0.5}
+       "rel_update_err": (num / max(den, 1e-30)) ** 0.5,
+       "step": {"local_batch": Bl, "prompts": Nmax, "original_size": [496, 512], "ms_per_step_max_over_ranks": ms_step,
+                "decoder_params": sum(p.numel() for p in dec), "grad_allreduce_bytes": st2.get("grad_allreduce_bytes"),
+                "grad_allreduce_ms": ms_ar,
+                "grad_allreduce_GBps": (st2.get("grad_allreduce_bytes") or 0) / max(ms_ar, 1e-9) / 1e6,
+                "note": "tiny random vision encoder + the real-size SAM mask decoder (no weights offline); "
+                        "postprocess_masks + dice_ce_loss + fused topo loss (interp=50) + SUM all-reduce of decoder gradients"}}
 gathered = [None] * world
 dist.all_gather_object(gathered, out)
 if rank == 0:

@@ -16,3 +16,22 @@ KATS = {
     "saddle": ([[1, 2, 3, 4, 5], [16, 30, 17, 31, 6], [15, 20, 18, 21, 7], [14, 13, 19, 9, 8], [10, 11, 12, 22, 23]],
                [(20, 22)], [(5, 8), (12, 6), (12, 17)], (0, 8)),
 }
+
+# Images that tell apart the two candidate H0 tie rules (oracle/oracle_literal.py, "KNOWN RISK"): the canonical
+# (value, dim, position) pairing this repo implements, and gudhi's union-find short cut for edges as recalled
+# [UPSTREAM-RECALL].  Two components with EQUAL minima merge through a higher edge: the diagram is the same,
+# the creator pixel is not.  Unverifiable here; tests/golden/make_golden_reference.py records the truth.
+TIE_KATS = {
+    "two_equal_minima": {
+        "image": [[1, 5, 1], [5, 5, 5], [5, 5, 5]],
+        "canonical": {"h0": [(2, 1)], "ess": (0, 1)},          # the later-positioned minimum (pixel 2) dies
+        "gudhi_union_find": {"h0": [(0, 1)], "ess": (2, 1)},   # the class of the edge's first vertex (pixel 0) dies
+        "h1": [],
+    },
+    "equal_minima_on_the_diagonal": {
+        "image": [[1, 5, 5], [5, 5, 5], [5, 5, 1]],
+        "canonical": {"h0": [(8, 4)], "ess": (0, 1)},
+        "gudhi_union_find": {"h0": [(0, 4)], "ess": (8, 1)},
+        "h1": [],
+    },
+}

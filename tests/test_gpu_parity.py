@@ -519,3 +519,19 @@ def test_double_backward_raises():
     (g,) = torch.autograd.grad(loss, p, create_graph=True)
     with pytest.raises(RuntimeError):
         g.sum().backward()
+
+
+@pytest.mark.timeout(600)
+def test_c5_scale_one_full_image():
+    """BASELINE configs[4] at its real resolution: every map of one full 14-class 1024x1024 image (prediction and
+    ground truth) bit-exact against the oracle, then loss and gradient of a 2-image batch within 1e-5."""
+    import os
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(1, 1024, 1024, seed=1234 + 5000)
+    _assert_same_pairs(torch.cat([pred[0], truth[0]]).numpy(), 1)
+    p2, t2 = torch.cat([pred, pred.flip(-2)]), torch.cat([truth, truth.flip(-2)])
+    loss, grad = _loss_and_grad(p2, t2, 0.1, feat_d=1)
+    want, wgrad, _ = oracle.topo_loss(p2.numpy(), t2.numpy(), 0.1, feat_d=1, nthreads=os.cpu_count() or 1)
+    assert abs(loss - want) <= REL * abs(want), (loss, want)
+    assert np.array_equal(grad != 0, wgrad != 0)
+    assert np.abs(grad - wgrad).max() <= REL * np.abs(wgrad).max()

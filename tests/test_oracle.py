@@ -191,3 +191,66 @@ def test_betti_curves_match_connected_component_counts(seed, levels):
         b1 = int(np.sum((flat[p1[:, 0]] <= t) & (t < flat[p1[:, 1]]))) if len(p1) else 0
         assert b0 == n_comp, (t, b0, n_comp)
         assert b1 == n_holes, (t, b1, n_holes)
+
+
+def test_h0_tie_rule_candidates_are_told_apart():
+    """The canonical pairing (implemented everywhere in this repo) and gudhi's recalled union-find short cut for
+    dimension 0 agree on tie-free maps and on the diagram VALUES always; they differ in the creator pixel when two
+    merging components have equal minima.  This pins which images would expose the difference."""
+    from oracle.oracle_literal import h0_pairs_gudhi_union_find
+    from tests.kats import KATS, TIE_KATS
+    for name, kat in TIE_KATS.items():
+        f = np.array(kat["image"], dtype=np.float32)
+        l0, l1, less = cubical_pairs_literal(f)
+        assert sorted(l0) == sorted(kat["canonical"]["h0"]) and less == kat["canonical"]["ess"] and l1 == kat["h1"], name
+        assert [tuple(x) for x in oracle.cubical_pairs(f, 0)] == l0 + [less]
+        g0, gess = h0_pairs_gudhi_union_find(f)
+        if kat["gudhi_union_find"] is not None:
+            assert sorted(g0) == sorted(kat["gudhi_union_find"]["h0"]) and gess == kat["gudhi_union_find"]["ess"], name
+        # same diagram either way
+        vals = lambda pairs: sorted((float(f.ravel()[a]), float(f.ravel()[b])) for a, b in pairs)
+        assert vals(g0) == vals(l0)
+    assert h0_pairs_gudhi_union_find(np.array(TIE_KATS["two_equal_minima"]["image"], np.float32))[0] != \
+        cubical_pairs_literal(np.array(TIE_KATS["two_equal_minima"]["image"], np.float32))[0]
+    rng = np.random.default_rng(0)
+    for _ in range(30):  # tie-free: identical
+        f = rng.permutation(49).reshape(7, 7).astype(np.float32)
+        l0, _, less = cubical_pairs_literal(f)
+        g0, gess = h0_pairs_gudhi_union_find(f)
+        assert g0 == l0 and gess == less
+    differ = []
+    for name, (img, h0, h1, ess) in KATS.items():
+        g0, gess = h0_pairs_gudhi_union_find(np.array(img, np.float32))
+        if len(set(np.array(img).ravel().tolist())) == np.array(img).size:  # all pixel values distinct: both rules agree
+            assert sorted(g0) == sorted(h0) and gess == ess, name
+        elif not (sorted(g0) == sorted(h0) and gess == ess):
+            differ.append(name)
+    # with tied pixel values even zero-persistence merges move the surviving creator under the recalled rule, so
+    # the essential class can land on another pixel of the same value (e.g. the all-zero background)
+    assert set(differ) <= {"two_diag_holes", "hole_touching_border", "nested"}
+
+
+def test_two_valued_h1_rule():
+    """csrc/ph_binary.cuh: on a map with two values the H1 pairs are the 4-connected hi blobs off the border,
+    destroyer = last raster pixel of the blob, creator = the pixel below it, in raster order of the destroyer."""
+    from scipy import ndimage as ndi
+    rng = np.random.default_rng(1)
+    for t in range(400):
+        n = int(rng.integers(2, 14))
+        f = (rng.random((n, n)) < rng.choice([0.05, 0.2, 0.5, 0.8, 0.95])).astype(np.float32)
+        if t % 3 == 1:
+            f = f * 3.5 - 1.25
+        if t % 3 == 2:
+            f = -f
+        want = oracle.cubical_pairs(f, 1)
+        got = []
+        if f.min() != f.max():
+            lab, k = ndi.label(f == f.max())
+            for i in range(1, k + 1):
+                ys, xs = np.nonzero(lab == i)
+                if ys.min() == 0 or xs.min() == 0 or ys.max() == n - 1 or xs.max() == n - 1:
+                    continue
+                p = int((ys * n + xs).max())
+                got.append((p + n, p))
+        got.sort(key=lambda x: x[1])
+        assert [tuple(x) for x in want.tolist()] == got
