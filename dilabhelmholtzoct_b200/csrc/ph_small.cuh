@@ -356,6 +356,84 @@ __device__ __forceinline__ void merge_lanes(const TRef& T, const CrossEdge* __re
 }
 
 
+
+// ---- one band of a multi-band map: merge the band's own crossing edges on a packed table in shared memory
+//      (band-local basin / edge ids) and move the resulting entries to the map's global 128-bit table; a band
+//      whose table does not fit the packed form hands its edges to the cross-band list instead.  Kept out of
+//      line: it runs once per band and must not cost the main path registers.
+struct BandMergeArgs {
+    unsigned char* smem;
+    CrossEdge* elist; size_t e_stride; int n_in;
+    TEntry* Tg; size_t k_stride; const uint32_t* zvalg;
+    int Kb, cid_base, H, W, bw, c0, top_reserved;
+    int* n_cross_band;
+};
+
+template <int DIM>
+__device__ __noinline__ void band_merge(const BandMergeArgs& B TL_SPARAM) {
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5;
+    const int Kb = B.Kb, cid_base = B.cid_base, bw = B.bw, GWb = 2 * B.bw + 1, GW = 2 * B.W + 1, n_in = B.n_in;
+    const int n_ids_b = B.H * GWb + bw;
+    const int Pb = 32 - __clz(n_ids_b), Gb = 32 - __clz(Kb + 1);
+    const size_t ring_b = (size_t)(((Kb + 1) * 8 + 15) & ~15) + (size_t)(((Kb + 1) * 4 + 15) & ~15);
+    const bool fits = Pb + Gb <= 32 && ring_b + (size_t)(kPhThreads / 32) * kRing * sizeof(CrossEdge) + (size_t)B.top_reserved <= (size_t)kSmallSmemBytes;
+    const uint32_t lowmask_b = (1u << (32 - Gb)) - 1u;
+    // band-local dense edge id -> global dense edge id (both order the band's edges like the bitmap does)
+    auto pos_global = [&](uint32_t pb) {
+        const uint32_t rr = pb / (uint32_t)GWb, rem = pb - rr * (uint32_t)GWb;
+        return rem < (uint32_t)bw ? rr * (uint32_t)GW + (uint32_t)B.c0 + rem : rr * (uint32_t)GW + (uint32_t)B.W + (uint32_t)B.c0 + (rem - (uint32_t)bw);
+    };
+    if (fits) {
+        uint64_t* T64b = reinterpret_cast<uint64_t*>(B.smem);
+        uint32_t* Z32b = reinterpret_cast<uint32_t*>(B.smem + (((Kb + 1) * 8 + 15) & ~15));
+        for (int cc = tid; cc <= Kb; cc += nt) {
+            T64b[cc] = (~0ull << Gb) | (uint32_t)cc;
+            Z32b[cc] = (cc && (size_t)(cid_base + cc) < B.k_stride) ? B.zvalg[cid_base + cc] : 0u;
+        }
+        __syncthreads();
+        Packed PKb;
+        PKb.t_s = (uint32_t)__cvta_generic_to_shared(B.smem);
+        PKb.z_s = PKb.t_s + (uint32_t)(((Kb + 1) * 8 + 15) & ~15);
+        PKb.G = Gb; PKb.gmask = (1u << Gb) - 1u;
+        const int perw = (n_in + (nt >> 5) - 1) / (nt >> 5);
+        const int wb = min(n_in, warp * perw), we = min(n_in, wb + perw);
+        merge_warpq_packed<DIM>(PKb, B.elist, wb, we, PKb.t_s + (uint32_t)ring_b + (uint32_t)warp * kRing * 16u, nullptr TL_SARG);
+        __syncthreads();
+        for (int cc = tid + 1; cc <= Kb; cc += nt) {  // global edge ids, global basin ids
+            if ((size_t)(cid_base + cc) >= B.k_stride) continue;
+            const uint64_t e = T64b[cc];
+            const uint64_t up = e >> Gb;
+            TEntry out;
+            out.zval = Z32b[cc];
+            if (up == (~0ull >> Gb)) { out.ekey = kRootKey; out.target = (uint32_t)(cid_base + cc); }
+            else {
+                const uint32_t idk = (uint32_t)up & lowmask_b;
+                const uint32_t pg = pos_global(DIM == 1 ? lowmask_b - idk : idk);
+                out.ekey = ((up >> (32 - Gb)) << 32) | (DIM == 1 ? ~pg : pg);
+                const uint32_t tl_ = (uint32_t)e & PKb.gmask;
+                out.target = tl_ ? (uint32_t)cid_base + tl_ : 0u;
+            }
+            B.Tg[cid_base + cc] = out;
+        }
+    } else {
+        for (int cc = tid + 1; cc <= Kb; cc += nt) {
+            if ((size_t)(cid_base + cc) >= B.k_stride) continue;
+            TEntry out;
+            out.ekey = kRootKey; out.target = (uint32_t)(cid_base + cc); out.zval = B.zvalg[cid_base + cc];
+            B.Tg[cid_base + cc] = out;
+        }
+        for (int i = tid; i < n_in; i += nt) {
+            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(B.elist + i));
+            const uint32_t pg = pos_global(DIM == 1 ? ~v.x : v.x);
+            const int ix = atomicAdd(B.n_cross_band, 1);
+            if ((size_t)ix + (size_t)n_in < B.e_stride)  // the tail never reaches the band's own list: e_stride has a band of slack
+                __stcg(reinterpret_cast<uint4*>(B.elist + (B.e_stride - 1 - (size_t)ix)),
+                       make_uint4(DIM == 1 ? ~pg : pg, v.y, v.z ? v.z + (uint32_t)cid_base : 0u, v.w ? v.w + (uint32_t)cid_base : 0u));
+        }
+    }
+    __syncthreads();
+}
+
 struct PhSmallArgs {
     PhArgs base;
     CrossEdge* elist;    // [grid][e_stride] edges that cross two basins
@@ -415,11 +493,13 @@ struct SmallCtx {
     }
 };
 
-template <int DIM>
-__global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) {
+// MULTI = false: the host guarantees a single band (<= 65536 pixels / <= 65535 vertices): the band loop runs
+// once and everything that serves band borders is compiled out of the headline kernel.
+template <int DIM, bool MULTI>
+__global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_constant__ PhSmallArgs S) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned int s_job, s_next;
-    __shared__ int s_count, s_K, s_ncross, s_nan;
+    __shared__ int s_count, s_K, s_ncross, s_nan, s_nx;
     __shared__ unsigned long long s_argmax;
     __shared__ unsigned int s_lo, s_hi;
     __shared__ int s_wcnt[kPhThreads / 32];
@@ -448,7 +528,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
     for (;;) {
         __syncthreads();
         // one job is always claimed ahead: its map is prefetched into L2 while this one is being emitted
-        if (tid == 0) { s_job = s_next; s_next = atomicAdd(A.job_counter, 1u); s_count = 0; s_ncross = 0; s_nan = 0; s_argmax = 0ull; s_lo = 0xFFFFFFFFu; s_hi = 0u; }
+        if (tid == 0) { s_job = s_next; s_next = atomicAdd(A.job_counter, 1u); s_count = 0; s_ncross = 0; s_nx = 0; s_nan = 0; s_argmax = 0ull; s_lo = 0xFFFFFFFFu; s_hi = 0u; }
         __syncthreads();
         const unsigned int job = s_job;
         if (job >= n_jobs) break;
@@ -547,10 +627,12 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         //      equal edges, H0: the edge above), so plateaus contract inside a band instead of leaving one
         //      sub-basin per column.
         const int rowlen = DIM == 1 ? W : VW, n_rows = DIM == 1 ? H : H + 1;
+        const int n_rows_all = n_rows;
         const bool alias = DIM == 1 && N == 65536;  // single band whose last pixel doubles as OUTSIDE
         const int cols_per_band = alias ? rowlen : fast ? min(rowlen, (65535 / n_rows) & ~3) : min(rowlen, 65535 / n_rows);
-        const bool one_band = cols_per_band >= rowlen;
-        uint32_t* prev_lab = reinterpret_cast<uint32_t*>(smem + kParBytes + kMaskBytes);  // labels of the previous band's last column
+        const bool one_band = !MULTI || cols_per_band >= rowlen;
+        // labels of the previous band's last column: at the top of shared memory, out of the way of the in-band table
+        uint32_t* prev_lab = reinterpret_cast<uint32_t*>(smem + kSmallSmemBytes - 4 * (size_t)(n_rows_all));
         CrossEdge* elist = S.elist + (size_t)blockIdx.x * S.e_stride;
         int cid_base = 0;  // basins found in earlier bands
         // pick(r, c): step (dr, dc) to the far end of node (r,c)'s earliest incident edge when that edge
@@ -604,6 +686,12 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 else elder_far = mono32(g.vertex_val(r + dr, c + dc, nullptr)) < (uint32_t)(best >> 32);
             }
         };
+        // Maps of several bands (fast front end): every band's own crossing edges are merged right away on a
+        // packed table in SHARED memory (band-local basin and edge ids), the resulting entries are written to
+        // the map's global table, and only the edges that cross a band border (one per row and border) are
+        // left for the final merge on that global table.  Exact for the same reason the merge accepts edges
+        // in any order: entries are facts, and a band's facts stay true in the whole map.
+        const bool inband = MULTI && fast && !one_band;
         if (fast) {
             // ================= fast front end =================
             // Every warp owns a contiguous chunk of whole 128-node groups; per trip a lane owns the 4
@@ -624,7 +712,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             const int trips = (wend - wbeg + 127) >> 7;                  // <= 16
             cx.bw = bw; cx.c0 = c0; cx.rowlen = W; cx.divB = divW;
             __syncthreads();  // the previous band's readers of par[] are done
-            if (tid == 0) par[kOut16] = (uint16_t)kOut16;  // OUTSIDE's own entry (alias: the last pixel)
+            if (tid == 0) { par[kOut16] = (uint16_t)kOut16; if (inband) s_ncross = 0; }  // OUTSIDE's own entry (alias: the last pixel)
             // ---- level 0a: pick pointers, min / max of the map, tie flags for level 0b
             {
                 float vlo = __int_as_float(0x7F800000), vhi = __int_as_float(0xFF800000);
@@ -818,24 +906,32 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             //      v-edge to its left and the h-edge above it (the left edge of a band's first column reaches
             //      into the previous band, whose last-column labels are kept in prev_lab); the last column /
             //      row also own the boundary edges to OUTSIDE.  Dense edge ids as in the generic path.
+            // Labels and dense edge ids are BAND-LOCAL (basin rank + 1, 0 = OUTSIDE; bitmap row pair i of the band
+            // holds its bw h-edges, then its bw + 1 v-edges): with a single band that is the global numbering.
+            // Only the left edge of a band's first column leaves the band: it goes, with global labels and a
+            // global edge id, to the cross-band list that grows down from the end of the CTA's list.
             auto glab = [&](uint32_t v) { return v == kOut16 ? 0u : (uint32_t)(cid_base + 1) + v; };
+            auto llab = [&](uint32_t v) { return v == kOut16 ? 0u : v + 1u; };
+            const int GWb = 2 * bw + 1;
             for (int t = 0; t < trips; ++t) {  // warp-uniform trip count
                 const int x = wbeg + t * 128 + lane * 4;
                 const bool valid = x < wend;
                 unsigned flags = 0u;
                 uint32_t lab[5] = {0u, 0u, 0u, 0u, 0u}, ulab[4] = {0u, 0u, 0u, 0u};  // lab[0]: left of the quad
                 float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, u[4] = {0.f, 0.f, 0.f, 0.f};
-                int r = 0, c = 0;
+                int r = 0, c = 0, cl = 0;
+                bool xband = false;  // the quad's left edge crosses into the previous band
                 if (valid) {
                     r = (int)divW.div((uint32_t)x);
-                    const int cl = x - r * bw;
+                    cl = x - r * bw;
                     c = c0 + cl;
+                    xband = MULTI && cl == 0 && c > 0;
                     const uint2 w = *reinterpret_cast<const uint2*>(par + x);
-                    lab[1] = glab(w.x & 0xFFFFu); lab[2] = glab(w.x >> 16); lab[3] = glab(w.y & 0xFFFFu); lab[4] = glab(w.y >> 16);
-                    if (c > 0) lab[0] = cl > 0 ? glab(par[x - 1]) : prev_lab[r];
+                    lab[1] = llab(w.x & 0xFFFFu); lab[2] = llab(w.x >> 16); lab[3] = llab(w.y & 0xFFFFu); lab[4] = llab(w.y >> 16);
+                    if (cl > 0) lab[0] = llab(par[x - 1]);
                     if (r > 0) {
                         const uint2 wu = *reinterpret_cast<const uint2*>(par + x - bw);
-                        ulab[0] = glab(wu.x & 0xFFFFu); ulab[1] = glab(wu.x >> 16); ulab[2] = glab(wu.y & 0xFFFFu); ulab[3] = glab(wu.y >> 16);
+                        ulab[0] = llab(wu.x & 0xFFFFu); ulab[1] = llab(wu.x >> 16); ulab[2] = llab(wu.y & 0xFFFFu); ulab[3] = llab(wu.y >> 16);
                     }
                     const float* q = f + r * W + c;
                     const float4 M = __ldg(reinterpret_cast<const float4*>(q));
@@ -848,10 +944,15 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t own = lab[k + 1];
-                        if (lab[k] != own) flags |= 1u << (4 * k);      // left v-edge (boundary edge when c + k == 0)
+                        if (lab[k] != own && !(k == 0 && xband)) flags |= 1u << (4 * k);  // left v-edge (boundary edge when c + k == 0)
                         if (ulab[k] != own) flags |= 2u << (4 * k);     // top h-edge (boundary edge when r == 0)
                         if (c + k == W - 1 && own != 0u) flags |= 4u << (4 * k);
                         if (r == H - 1 && own != 0u) flags |= 8u << (4 * k);
+                    }
+                    if (xband) {  // always crossing: level-0 links never leave a band
+                        const int ix = atomicAdd(&s_nx, 1);
+                        const uint32_t posg = (uint32_t)(r * GW + W + c);
+                        if (ix < (int)S.e_stride) store_edge(elist + (S.e_stride - 1 - (size_t)ix), g.make_ekey(fminf(m[0], m[1]), posg), prev_lab[r], glab(w.x & 0xFFFFu));
                     }
                 }
                 const int cnt = __popc(flags);
@@ -871,10 +972,10 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                             if (flags & (1u << (4 * k + e))) {
                                 uint32_t lo, pos;
                                 float val;
-                                if (e == 0) { lo = lab[k]; pos = (uint32_t)(r * GW + W + c + k); val = c + k == 0 ? fp : fminf(m[k], fp); }
-                                else if (e == 1) { lo = ulab[k]; pos = (uint32_t)(r * GW + c + k); val = r == 0 ? fp : fminf(u[k], fp); }
-                                else if (e == 2) { lo = 0u; pos = (uint32_t)(r * GW + 2 * W); val = fp; }
-                                else { lo = 0u; pos = (uint32_t)(H * GW + c + k); val = fp; }
+                                if (e == 0) { lo = lab[k]; pos = (uint32_t)(r * GWb + bw + cl + k); val = c + k == 0 ? fp : fminf(m[k], fp); }
+                                else if (e == 1) { lo = ulab[k]; pos = (uint32_t)(r * GWb + cl + k); val = r == 0 ? fp : fminf(u[k], fp); }
+                                else if (e == 2) { lo = 0u; pos = (uint32_t)(r * GWb + 2 * bw); val = fp; }
+                                else { lo = 0u; pos = (uint32_t)(H * GWb + cl + k); val = fp; }
                                 if (slot < (int)S.e_stride) store_edge(elist + slot, g.make_ekey(val, pos), lo, own);
                                 ++slot;
                             }
@@ -886,8 +987,18 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
             // labels of this band's last column, for the next band's "left" edges
             if (c1 < W)
                 for (int r = tid; r < H; r += nt) prev_lab[r] = glab(par[r * bw + bw - 1]);
-            cid_base += Kb;
             TL_PROF(6);
+            if (inband) {
+                __syncthreads();  // prev_lab is written and every label has been read: the band's table may take the space
+                BandMergeArgs bm;
+                bm.smem = smem; bm.elist = elist; bm.e_stride = S.e_stride; bm.n_in = min(s_ncross, (int)S.e_stride);
+                bm.Tg = S.T2g + (size_t)blockIdx.x * S.k_stride; bm.k_stride = S.k_stride; bm.zvalg = zvalg;
+                bm.Kb = Kb; bm.cid_base = cid_base; bm.H = H; bm.W = W; bm.bw = bw; bm.c0 = c0; bm.top_reserved = 4 * n_rows_all;
+                bm.n_cross_band = &s_nx;
+                band_merge<DIM>(bm TL_SARG);
+                TL_PROF(4);
+            }
+            cid_base += Kb;
             }  // bands
             if (fast_one && (s_lo == s_hi || s_nan)) {  // block-uniform: constant map, or a NaN pixel (pairing undefined)
                 if (tid == 0) { int avail; if (s_nan) atomicOr(A.ps.status, kStNonFinite); ps_reserve(A.ps, set, map, 0, &avail); A.ps.dsum[set][map] = 0.0; }
@@ -1120,8 +1231,9 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         const int n_edge_ids = H * GW + W;  // dense ids 0 .. H*(2W+1)+W-1
         const int Pbits = 32 - __clz(n_edge_ids), Gbits = 32 - __clz(K + 1);
         const size_t ring_off = (size_t)(((K + 1) * 8 + 15) & ~15) + (size_t)(((K + 1) * 4 + 15) & ~15);
-        const bool packed = Pbits + Gbits <= 32 && ring_off + (size_t)(kPhThreads / 32) * kRing * sizeof(CrossEdge) <= (size_t)kSmallSmemBytes;
-        const bool t_in_smem = K + 1 <= t_cap_smem;
+        // (maps merged band by band already hold their entries in the global table: 128-bit form, global memory)
+        const bool packed = !inband && Pbits + Gbits <= 32 && ring_off + (size_t)(kPhThreads / 32) * kRing * sizeof(CrossEdge) <= (size_t)kSmallSmemBytes;
+        const bool t_in_smem = !inband && K + 1 <= t_cap_smem;
         TRef T;
         T.g = t_in_smem ? Ts : S.T2g + (size_t)blockIdx.x * S.k_stride;
         T.s = (uint32_t)__cvta_generic_to_shared(Ts);
@@ -1145,6 +1257,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
                 T64[c] = (~0ull << Gbits) | (uint32_t)c; Z32[c] = c ? zvalg[c] : 0u;
                 if (rp_smem) { const uint32_t rp = c ? rootpix[c] : 0u; if (rp16) rp_s16[c] = (uint16_t)rp; else rp_s32[c] = rp; }
             }
+        } else if (inband) {
+            if (tid == 0) { TEntry e; e.ekey = kRootKey; e.target = 0u; e.zval = 0u; T.g[0] = e; }  // OUTSIDE; the bands wrote the rest
         } else {
             for (int c = tid; c <= K; c += nt) {
                 TEntry e;
@@ -1160,7 +1274,9 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(PhSmallArgs S) 
         // independent 16-byte loads in flight), so lanes stay converged instead of serialising
         // differently long walks.
         {
-            const int n_cross = s_ncross;
+            // in-band mode: what is left are the edges across band borders, at the END of the CTA's list
+            const int n_cross = inband ? min(s_nx, (int)S.e_stride) : min(s_ncross, (int)S.e_stride);
+            if (inband) elist += S.e_stride - (size_t)n_cross;
             const uint32_t* tie_root = one_band ? nullptr : rootpix;
             if (packed) {  // contiguous slice per warp, edges handed to idle lanes
                 const int perw = (n_cross + (nt >> 5) - 1) / (nt >> 5);

@@ -174,6 +174,9 @@ ScratchLayout make_scratch(int H, int W, int dim, bool with_sort, unsigned long 
         const size_t n_real = dim == 1 ? (size_t)H * W : (size_t)(H + 1) * (W + 1);
         L.e_stride = align_up(n_edges - n_real + L.k_stride + 64, 64);
         if (L.e_stride > align_up(n_edges, 64)) L.e_stride = align_up(n_edges, 64);
+        // maps of several bands keep one band's own list at the front and the cross-band list at the back of
+        // the same buffer: one band of slack (a band has < 2 * 65536 edges) keeps them apart
+        if (L.n_nodes > 65537) L.e_stride += 2 * 65536 + 64;
         L.elist = take(sizeof(tl::CrossEdge) * L.e_stride * L.slots);
     }
     if (!L.small || force_global) {
@@ -254,13 +257,17 @@ int launch_ph(const float* m0, const float* m1, int n_sets, int M, const tl::Pai
         sa.elist = at<tl::CrossEdge>(scratch, L.elist); sa.e_stride = L.e_stride;
         sa.prof = opt(TL_OPT_PROFILE) ? at<unsigned long long>(state, 64) : nullptr;
         sa.binary_path = !opt(TL_OPT_NO_BINARY_PATH);
-        if (dim == 1) {
-            TL_CUDA(cudaFuncSetAttribute(tl::ph_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl::kSmallSmemBytes));
-            tl::ph_small_kernel<1><<<grid, tl::kPhThreads, tl::kSmallSmemBytes, st>>>(sa);
-        } else {
-            TL_CUDA(cudaFuncSetAttribute(tl::ph_small_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl::kSmallSmemBytes));
-            tl::ph_small_kernel<0><<<grid, tl::kPhThreads, tl::kSmallSmemBytes, st>>>(sa);
-        }
+        // single band: at most 65536 pixels (H1; the last pixel doubles as OUTSIDE) / 65535 vertices (H0)
+        const bool single = dim == 1 ? (long long)H * W <= 65536 : (long long)(H + 1) * (W + 1) <= 65535;
+        auto launch = [&](auto kernel) -> int {
+            TL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tl::kSmallSmemBytes));
+            kernel<<<grid, tl::kPhThreads, tl::kSmallSmemBytes, st>>>(sa);
+            return TL_OK;
+        };
+        int rc;
+        if (dim == 1) rc = single ? launch(tl::ph_small_kernel<1, false>) : launch(tl::ph_small_kernel<1, true>);
+        else rc = single ? launch(tl::ph_small_kernel<0, false>) : launch(tl::ph_small_kernel<0, true>);
+        if (rc != TL_OK) return rc;
     } else {
         const int grid = (int)(jobs < kPhSlots ? jobs : kPhSlots);
         if (dim == 1) tl::ph_kernel<1><<<grid, tl::kPhThreads, 0, st>>>(a);
