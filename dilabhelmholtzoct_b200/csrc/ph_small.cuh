@@ -211,7 +211,7 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
                                                    uint32_t ring_s, const uint32_t* tie_root TL_SPARAM) {
     const int lane = threadIdx.x & 31;
     const int G = T.G;
-    const uint64_t root_u = ~0ull >> G;              // upper part of a live basin's entry
+    const uint64_t gmask64 = (uint64_t)T.gmask;
     const uint32_t lowmask = (1u << (32 - G)) - 1u;  // the ordered dense edge id fits 32 - G bits
     // The slice is cut into 32 sub-slices of S records, lane l fetches from sub-slice l: a batch of 32 edges
     // is 32 edges that lie S records (tens of pixels) apart, so the edges the warp works on concurrently
@@ -222,7 +222,9 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
     const int total = S << 5;
     int cons = 0, avail = 0, issued = 0;
     uint32_t x = 0u, y = 0u;
-    uint64_t su = 0ull, ea = 0ull, eb = 0ull;
+    // sug = [ordered value 32 | ordered edge id | all-ones target]: an entry e (same layout, real target) was recorded
+    // at a LATER level than this edge iff e > sug -- one 64-bit compare per hop, no shifts
+    uint64_t sug = 0ull, ea = 0ull, eb = 0ull;
     bool active = false, doneA = true, doneB = true;
 #define TL_ISSUE()                                                                              \
     do {                                                                                        \
@@ -249,7 +251,7 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
                 uint32_t k0, k1, la, lb;
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(k0), "=r"(k1), "=r"(la), "=r"(lb) : "r"(a_) : "memory");
                 x = la; y = lb;
-                su = ((uint64_t)k1 << (32 - G)) | (k0 & lowmask);  // [ordered value 32 | ordered edge id]
+                sug = ((uint64_t)k1 << 32) | ((uint64_t)(k0 & lowmask) << G) | gmask64;
                 doneA = doneB = false; active = true;
                 TL_STAT(1);
             }
@@ -267,8 +269,8 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
             for (int hop = 0; hop < kHopsPerIter; ++hop) {  // several hops per trip through the loop's vote / refill logic
                 if (!doneA) { TL_STAT(0); ea = pk_load(T.t_s + x * 8u); }
                 if (!doneB) { TL_STAT(0); eb = pk_load(T.t_s + y * 8u); }
-                if (!doneA) { if ((ea >> G) > su) doneA = true; else x = (uint32_t)ea & T.gmask; }
-                if (!doneB) { if ((eb >> G) > su) doneB = true; else y = (uint32_t)eb & T.gmask; }
+                if (!doneA) { if (ea > sug) doneA = true; else x = (uint32_t)ea & T.gmask; }
+                if (!doneB) { if (eb > sug) doneB = true; else y = (uint32_t)eb & T.gmask; }
             }
             if (doneA && doneB) {
                 TL_STAT(2);
@@ -280,12 +282,12 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
                     const bool sw = basin_elder<DIM>(y, zy, x, zx, tie_root);
                     const uint32_t xx = sw ? y : x, yy = sw ? x : y;  // yy: the younger representative
                     const uint64_t ey = sw ? ea : eb;
-                    if (pk_cas(T.t_s + yy * 8u, ey, (su << G) | xx)) {
-                        if ((ey >> G) == root_u) {
+                    if (pk_cas(T.t_s + yy * 8u, ey, (sug & ~gmask64) | xx)) {
+                        if ((ey | gmask64) == ~0ull) {
                             active = false;
                         } else {  // re-assert yy's former connection for xx
                             TL_STAT(4);
-                            x = xx; y = (uint32_t)ey & T.gmask; su = ey >> G; doneA = doneB = false;
+                            x = xx; y = (uint32_t)ey & T.gmask; sug = ey | gmask64; doneA = doneB = false;
                         }
                     } else {
                         TL_STAT(5);
