@@ -17,6 +17,7 @@
 #pragma once
 #include "ph_kernel.cuh"
 #include "ph_binary.cuh"
+#include "match_small.cuh"
 
 namespace tl {
 
@@ -25,7 +26,7 @@ constexpr uint32_t kOut16 = 0xFFFFu;
 constexpr uint64_t kRootKey = ~0ull;
 constexpr int kParBytes = 65536 * 2;
 constexpr int kMaskBytes = 65536 / 8;
-constexpr int kSmallSmemBytes = 226 * 1024;  // dynamic shared memory of ph_small_kernel
+constexpr int kSmallSmemBytes = 223 * 1024;  // dynamic shared memory of ph_small_kernel (+ ~3.5 KB static: 227 KB per CTA)
 
 struct __align__(16) TEntry {
     uint64_t ekey;    // key of the edge at which this basin dies (kRootKey: still alive)
@@ -121,22 +122,22 @@ __device__ __forceinline__ int edge_top_eid(const Geo<DIM>& g, uint32_t eid, con
     return rem < g.W ? g.hedge_top(i, rem) : g.vedge_top(i, rem - g.W);
 }
 
-// same, also returning the map value at that pixel (it is one of the two values just compared)
+// same for an edge whose VALUE is known (it sits in the table entry): the upper / left pixel is the coface iff it
+// attains that value, so ONE map load decides instead of two
 template <int DIM>
-__device__ __forceinline__ void edge_top_pv(const Geo<DIM>& g, uint32_t eid, const FastDiv& divRW, int& pix, float& val) {
+__device__ __forceinline__ int edge_top_known(const Geo<DIM>& g, uint32_t eid, const FastDiv& divRW, float val) {
     const int RW = 2 * g.W + 1, W = g.W, H = g.H;
     const int i = (int)divRW.div(eid), rem = (int)eid - i * RW;
     if (rem < W) {  // h-edge(i, j) between pixels (i-1, j), (i, j)
         const int j = rem;
-        if (i == 0) { pix = j; val = g.px(0, j); }
-        else if (i == H) { pix = (H - 1) * W + j; val = g.px(H - 1, j); }
-        else { const float a = g.px(i - 1, j), b = g.px(i, j); if (a <= b) { pix = (i - 1) * W + j; val = a; } else { pix = i * W + j; val = b; } }
-    } else {        // v-edge(i, j) between pixels (i, j-1), (i, j)
-        const int j = rem - W;
-        if (j == 0) { pix = i * W; val = g.px(i, 0); }
-        else if (j == W) { pix = i * W + W - 1; val = g.px(i, W - 1); }
-        else { const float a = g.px(i, j - 1), b = g.px(i, j); if (a <= b) { pix = i * W + j - 1; val = a; } else { pix = i * W + j; val = b; } }
+        if (i == 0) return j;
+        if (i == H) return (H - 1) * W + j;
+        return g.px(i - 1, j) == val ? (i - 1) * W + j : i * W + j;
     }
+    const int j = rem - W;  // v-edge(i, j) between pixels (i, j-1), (i, j)
+    if (j == 0) return i * W;
+    if (j == W) return i * W + W - 1;
+    return g.px(i, j - 1) == val ? i * W + j - 1 : i * W + j;
 }
 
 // ---- packed triplet table: one 64-bit word per basin
@@ -446,6 +447,11 @@ struct PhSmallArgs {
     size_t k_stride;
     unsigned long long* prof;  // optional [8] phase cycle counters
     int binary_path;           // 1: try the two-valued fast path first (H1)
+    // tl_forward only: CTAs that have run out of persistence jobs match the maps whose two diagrams are complete
+    // (ready[k] == 2), so the matching runs in the tail of this launch instead of a launch of its own
+    int fuse_match;
+    unsigned int* ready;       // [n_maps] sets of map k that are finished (device counters, zeroed by the host)
+    MatchFwdArgs mf;
 };
 
 template <int DIM>
@@ -527,8 +533,11 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
     } while (0)
 
     if (tid == 0) s_next = atomicAdd(A.job_counter, 1u);
+    int finished_map = -1;  // (thread 0) map of the job just completed, to be published
     for (;;) {
         __syncthreads();
+        // publish the finished job: every thread's records are written (barrier above), release them device-wide
+        if (tid == 0 && finished_map >= 0 && S.fuse_match) { __threadfence(); atomicAdd(S.ready + finished_map, 1u); }
         // one job is always claimed ahead: its map is prefetched into L2 while this one is being emitted
         if (tid == 0) { s_job = s_next; s_next = atomicAdd(A.job_counter, 1u); s_count = 0; s_ncross = 0; s_nx = 0; s_nan = 0; s_argmax = 0ull; s_lo = 0xFFFFFFFFu; s_hi = 0u; }
         __syncthreads();
@@ -537,6 +546,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
         if (S.prof && tid == 0) t0 = clock64();
         // all prediction maps first (heavy), ground-truth maps (light) fill the tail of the launch
         const int set = (int)(job / (unsigned)A.n_maps), map = (int)(job % (unsigned)A.n_maps);
+        finished_map = map;
         // two-valued maps (one-hot ground truth): run-based labelling on a bit mask, no merge tree; a probe of
         // the first words sends every other map on to the generic path
         if (DIM == 1 && S.binary_path &&
@@ -1388,13 +1398,17 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
                         rec4[u].d = __ldg(g.f + rec4[u].des);
                         sk4[u] = ~0ull;
                     } else if (DIM == 1) {
+                        // birth / death values come out of the table (exact inverse of the ordered keys): the only
+                        // map access left is the one load that tells which pixel of the edge attains its value
                         rec4[u].des = x;
-                        rec4[u].d = __ldg(g.f + x);
-                        edge_top_pv<DIM>(g, (uint32_t)(~ek4[u]), divRW, rec4[u].cre, rec4[u].b);
+                        rec4[u].d = unmono32(~zv4[u]);
+                        rec4[u].b = unmono32(~(uint32_t)(ek4[u] >> 32));
+                        rec4[u].cre = edge_top_known<DIM>(g, (uint32_t)(~ek4[u]), divRW, rec4[u].b);
                         sk4[u] = ((uint64_t)(~zv4[u]) << 32) | (uint32_t)x;  // death cell = square x
                     } else {
                         { const int vi = (int)divVW.div((uint32_t)x); rec4[u].b = g.vertex_val(vi, x - vi * VW, &rec4[u].cre); }
-                        edge_top_pv<DIM>(g, (uint32_t)ek4[u], divRW, rec4[u].des, rec4[u].d);
+                        rec4[u].d = unmono32((uint32_t)(ek4[u] >> 32));
+                        rec4[u].des = edge_top_known<DIM>(g, (uint32_t)ek4[u], divRW, rec4[u].d);
                         sk4[u] = ek4[u];  // death cell = edge
                     }
                 }
@@ -1413,6 +1427,27 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
             if (tid == 0) A.ps.dsum[set][map] = dacc;
         }
         TL_PROF(5);
+    }
+    // ---- tail of the launch: this SM has no persistence job left.  Match the maps whose prediction and ground-truth
+    //      diagrams are both complete (the other SMs are still finishing theirs), one map per claim.
+    if (S.fuse_match) {
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) s_job = atomicAdd(S.mf.counter, 1u);
+            __syncthreads();
+            const int k = (int)s_job;
+            if (k >= S.mf.n_maps) break;
+            if (tid == 0) {
+                unsigned int v;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(S.ready + k) : "memory");
+                    if (v >= 2u) break;
+                    __nanosleep(200);
+                }
+            }
+            __syncthreads();
+            match_one_map(S.mf, k, reinterpret_cast<float2*>(smem));
+        }
     }
 #undef TL_PROF
 }

@@ -91,6 +91,11 @@ __device__ __forceinline__ uint32_t mono32(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// inverse of mono32 (exact; the two zeros both come back as +0.0)
+__device__ __forceinline__ float unmono32(uint32_t m) {
+    return __uint_as_float((m & 0x80000000u) ? (m & 0x7FFFFFFFu) : ~m);
+}
+
 __device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t* p) {
     return __ldcg(reinterpret_cast<const unsigned long long*>(p));
 }

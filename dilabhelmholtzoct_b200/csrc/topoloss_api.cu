@@ -45,6 +45,7 @@ struct Options {
         v[TL_OPT_PROFILE] = env1("TL_PROFILE");
         v[TL_OPT_NO_BINARY_PATH] = env1("TL_NO_BINARY");
         v[TL_OPT_WORST_CASE_WORKSPACE] = env1("TL_WORST_CASE_WORKSPACE");
+        v[TL_OPT_NO_FUSED_MATCH] = env1("TL_NO_FUSED_MATCH");
     }
 };
 Options g_opt;
@@ -109,7 +110,7 @@ int sm_count() {  // per call: the device may differ between calls (one process,
 //           [24] match work counter (u32) | [64..127] phase cycle counters (8 x u64)
 struct StateLayout {
     int M;
-    size_t counts[2], offs[2], dsum[2], cost, tpers, coef, heavy, arena, fixed;
+    size_t counts[2], offs[2], dsum[2], cost, tpers, coef, heavy, ready, arena, fixed;
     unsigned long long arena_default;  // records tl_workspace_bytes asks for
 };
 StateLayout make_state(int M, int H, int W, int dim, int B) {
@@ -125,6 +126,7 @@ StateLayout make_state(int M, int H, int W, int dim, int B) {
     L.tpers = take(sizeof(double) * (size_t)M);
     L.coef = take(sizeof(double) * (size_t)(B > 0 ? B : 1));
     L.heavy = take(sizeof(int32_t) * (size_t)M);
+    L.ready = take(sizeof(uint32_t) * (size_t)M);
     L.arena = o;
     L.fixed = o;
     // Records for both sets together.  Worst case: max_pairs per map and set.  Typical: noise-like
@@ -232,8 +234,12 @@ tl::PairStore pair_store(void* state, const StateLayout& L, size_t state_bytes, 
     return ps;
 }
 
+// mf != null: the shared-memory kernel also runs the matching (tl::match_one_map) in the tail of its launch;
+// *fused tells the caller whether it did (the global-memory kernel does not)
 int launch_ph(const float* m0, const float* m1, int n_sets, int M, const tl::PairStore& ps, const ScratchLayout& L, int H, int W,
-              int dim, void* state, void* scratch, cudaStream_t st) {
+              int dim, void* state, void* scratch, cudaStream_t st, const tl::MatchFwdArgs* mf = nullptr, unsigned int* ready = nullptr,
+              bool* fused = nullptr) {
+    if (fused) *fused = false;
     tl::PhArgs a;
     a.maps[0] = m0; a.maps[1] = m1;
     a.ps = ps;
@@ -257,6 +263,13 @@ int launch_ph(const float* m0, const float* m1, int n_sets, int M, const tl::Pai
         sa.elist = at<tl::CrossEdge>(scratch, L.elist); sa.e_stride = L.e_stride;
         sa.prof = opt(TL_OPT_PROFILE) ? at<unsigned long long>(state, 64) : nullptr;
         sa.binary_path = !opt(TL_OPT_NO_BINARY_PATH);
+        sa.fuse_match = mf != nullptr && !opt(TL_OPT_NO_FUSED_MATCH);
+        sa.ready = ready;
+        if (sa.fuse_match) {
+            sa.mf = *mf;
+            TL_CUDA(cudaMemsetAsync(ready, 0, sizeof(uint32_t) * (size_t)M, st));
+            if (fused) *fused = true;
+        } else memset(&sa.mf, 0, sizeof(sa.mf));
         // single band: at most 65536 pixels (H1; the last pixel doubles as OUTSIDE) / 65535 vertices (H0)
         const bool single = dim == 1 ? (long long)H * W <= 65536 : (long long)(H + 1) * (W + 1) <= 65535;
         auto launch = [&](auto kernel) -> int {
@@ -393,19 +406,21 @@ int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W
     tm.mark(0, st);
     // pairs leave the persistence kernel in a deterministic (raster) order, so the matching needs no
     // sort; the segmented sort only serves tl_persistence_pairs (gudhi's emission order)
-    rc = launch_ph(pred, truth, 2, M, ps, L, H, W, feat_d, state, scratch, st);
-    if (rc != TL_OK) return rc;
-    tm.mark(1, st);
-    tm.mark(2, st);
-
     tl::MatchFwdArgs mf;
     mf.ps = ps; mf.n_maps = M; mf.loss_r = loss_r; mf.q = q;
     mf.cost = at<double>(state, S.cost); mf.tpers = at<double>(state, S.tpers);
     mf.heavy = at<int32_t>(state, S.heavy); mf.n_heavy = at<unsigned int>(state, 20);
     mf.counter = at<unsigned int>(state, 24);
-    TL_CUDA(cudaFuncSetAttribute(tl::match_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tl::kColCache * 8));
-    tl::match_small_kernel<<<M < kMatchSlots ? M : kMatchSlots, tl::kMatchThreads, tl::kColCache * 8, st>>>(mf);
-    TL_CUDA(cudaGetLastError());
+    bool fused = false;
+    rc = launch_ph(pred, truth, 2, M, ps, L, H, W, feat_d, state, scratch, st, &mf, at<unsigned int>(state, S.ready), &fused);
+    if (rc != TL_OK) return rc;
+    tm.mark(1, st);
+    tm.mark(2, st);
+    if (!fused) {  // global-memory persistence kernel (or the fusion switched off): the matching gets its own launch
+        TL_CUDA(cudaFuncSetAttribute(tl::match_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tl::kColCache * 8));
+        tl::match_small_kernel<<<M < kMatchSlots ? M : kMatchSlots, tl::kMatchThreads, tl::kColCache * 8, st>>>(mf);
+        TL_CUDA(cudaGetLastError());
+    }
     {   // maps with two large diagrams (none for segmentation ground truth): general kernel, global scratch
         tl::MatchArgs m;
         const char* recs = reinterpret_cast<const char*>(ps.arena) + offsetof(tl::PairRec, b);

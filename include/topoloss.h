@@ -56,7 +56,7 @@ const char* tl_last_error(void);
 
 /*
  * Process-wide options.  Initial values are read from the environment ONCE, when the library is
- * loaded (TL_FORCE_GLOBAL, TL_PROFILE, TL_NO_BINARY, TL_WORST_CASE_WORKSPACE = "1"); tl_set_option
+ * loaded (TL_FORCE_GLOBAL, TL_PROFILE, TL_NO_BINARY, TL_WORST_CASE_WORKSPACE, TL_NO_FUSED_MATCH = "1"); tl_set_option
  * changes them afterwards.  FORCE_GLOBAL_KERNEL and WORST_CASE_WORKSPACE change the workspace layout:
  * use the same setting for tl_workspace_bytes and the calls that consume its sizes.
  */
@@ -64,7 +64,8 @@ const char* tl_last_error(void);
 #define TL_OPT_PROFILE 1              /* accumulate per-phase cycle counters (tl_debug_profile) */
 #define TL_OPT_NO_BINARY_PATH 2       /* measurement: two-valued maps through the generic path */
 #define TL_OPT_WORST_CASE_WORKSPACE 3 /* size every table for the worst case: no input can overflow */
-#define TL_OPT_COUNT_ 4
+#define TL_OPT_NO_FUSED_MATCH 4       /* measurement: matching in a launch of its own instead of the persistence kernel's tail */
+#define TL_OPT_COUNT_ 5
 int tl_set_option(int which, int value);
 int tl_get_option(int which);
 
