@@ -38,6 +38,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_variant(name: str, defines) -> str:
+    """Experiment build: libtopoloss_<name>.so with extra -D flags (select it with TL_LIB_PATH)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out = os.path.join(_HERE, f"libtopoloss_{name}.so")
+    subprocess.check_call([nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out, os.path.join(CSRC, "topoloss_api.cu")], cwd=CSRC)
+    return out
+
+
 def build_stats() -> str:
     """Debug build with merge event counters (-DTL_STATS); used by scripts/stats_probe.py only."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -732,6 +732,15 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
                 for (int t = 0; t < trips; ++t) {
                     const int x = wbeg + t * 128 + lane * 4;  // band-local id of the quad
                     unsigned defer = 0u;
+#ifdef TL_PREFETCH_L1
+                    if (lane < 12 && t + 1 < trips) {  // next trip's three half rows (4 lines each) into L1
+                        const int xn = wbeg + (t + 1) * 128 + (lane & 3) * 32;
+                        if (xn < wend) {
+                            const int rn = (int)divW.div((uint32_t)xn) + (lane >> 2) - 1;
+                            if (rn >= 0 && rn < H) asm volatile("prefetch.global.L1 [%0];" :: "l"(f + (size_t)rn * W + c0 + (xn - (rn - (lane >> 2) + 1) * bw)));
+                        }
+                    }
+#endif
                     if (x < wend) {
                         const int r = (int)divW.div((uint32_t)x), cl = x - r * bw, c = c0 + cl;
                         const float* q = f + r * W + c;
@@ -929,6 +938,15 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
                 const int x = wbeg + t * 128 + lane * 4;
                 const bool valid = x < wend;
                 unsigned flags = 0u;
+#ifdef TL_PREFETCH_L1
+                if (lane < 8 && t + 1 < trips) {  // next trip's two half rows (own row, row above) into L1
+                    const int xn = wbeg + (t + 1) * 128 + (lane & 3) * 32;
+                    if (xn < wend) {
+                        const int r0 = (int)divW.div((uint32_t)xn), rn = r0 - (lane >> 2);
+                        if (rn >= 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(f + (size_t)rn * W + c0 + (xn - r0 * bw)));
+                    }
+                }
+#endif
                 uint32_t lab[5] = {0u, 0u, 0u, 0u, 0u}, ulab[4] = {0u, 0u, 0u, 0u};  // lab[0]: left of the quad
                 float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, u[4] = {0.f, 0.f, 0.f, 0.f};
                 int r = 0, c = 0, cl = 0;

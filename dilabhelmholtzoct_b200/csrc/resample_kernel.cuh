@@ -265,4 +265,152 @@ __global__ void __launch_bounds__(256) postprocess_bwd_kernel(PostArgs a, int ti
     }
 }
 
+// Backward as a GATHER (no atomics, no zero fill): a CTA owns a kGT_Y x kGT_X tile of SOURCE pixels.  Both
+// stages are separable and monotone in the index, so the output pixels that read source column s form one
+// interval [lo(s), hi(s)] (found by bisection on the forward's own tap formula), likewise for rows; the tile's
+// window of grad_out is staged in shared memory once, reduced along x with the composite column weights into
+// T[row][source column], then along y.  Every source pixel is written exactly once.
+// (Down-sampling to the original size, the reference's case: ~6 taps per axis and source pixel.  When the
+// output is much larger than the source the taps per source pixel grow and the host keeps the scatter kernel.)
+constexpr int kGT_Y = 8, kGT_X = 32, kGK = 16, kGWR = 40, kGWC = 104, kGRows = 256;
+constexpr int kGTileRows = 2 * kGT_Y;  // source rows per tile: every thread produces two of them
+
+// weight of source index s in output index o along one axis: two bilinear stages, ATen's align_corners=False
+__device__ __forceinline__ float post_axis_weight(float s2, int mid_in, float s1, int src_in, int o, int s) {
+    int Y0, Y1, a0, a1; float l0, l1, p0, p1;
+    half_pixel(s2, o, mid_in, Y0, Y1, l0, l1);
+    half_pixel(s1, Y0, src_in, a0, a1, p0, p1);
+    float w = l0 * ((a0 == s ? p0 : 0.f) + (a1 == s ? p1 : 0.f));
+    half_pixel(s1, Y1, src_in, a0, a1, p0, p1);
+    return w + l1 * ((a0 == s ? p0 : 0.f) + (a1 == s ? p1 : 0.f));
+}
+// first / last source index an output index reads (monotone non-decreasing in o)
+__device__ __forceinline__ int post_src_lo(float s2, int mid_in, float s1, int src_in, int o) {
+    int Y0, Y1, a0, a1; float l0, l1;
+    half_pixel(s2, o, mid_in, Y0, Y1, l0, l1);
+    half_pixel(s1, Y0, src_in, a0, a1, l0, l1);
+    return a0;
+}
+__device__ __forceinline__ int post_src_hi(float s2, int mid_in, float s1, int src_in, int o) {
+    int Y0, Y1, a0, a1; float l0, l1;
+    half_pixel(s2, o, mid_in, Y0, Y1, l0, l1);
+    half_pixel(s1, Y1, src_in, a0, a1, l0, l1);
+    return a1;
+}
+// [lo, hi] of the output indices that may read source index s (empty: hi < lo)
+__device__ __forceinline__ void post_out_range(float s2, int mid_in, float s1, int src_in, int n_out, int s, int& lo, int& hi) {
+    int a = 0, b = n_out;  // smallest o with src_hi(o) >= s
+    while (a < b) { const int m = (a + b) >> 1; if (post_src_hi(s2, mid_in, s1, src_in, m) >= s) b = m; else a = m + 1; }
+    lo = a;
+    a = -1; b = n_out - 1;  // largest o with src_lo(o) <= s
+    while (a < b) { const int m = (a + b + 1) >> 1; if (post_src_lo(s2, mid_in, s1, src_in, m) <= s) a = m; else b = m - 1; }
+    hi = a;
+}
+
+// A job is a STRIP: one map, kGT_X source columns, up to kGRows source rows.  The strip's column ranges and
+// weights and ALL its row ranges and weights are computed once (one thread per row / column), then the CTA walks
+// down the strip in tiles of kGT_Y rows: stage the tile's window of grad_out, reduce along x, reduce along y.
+__global__ void __launch_bounds__(kGT_Y * kGT_X) postprocess_bwd_gather_kernel(PostArgs a, int chunks_y, int tiles_x) {
+    __shared__ float gw[kGWR][kGWC + 1];
+    __shared__ float Tt[kGWR][kGT_X];
+    __shared__ float wx[kGT_X][kGK], wy[kGRows][kGK];
+    __shared__ int xlo[kGT_X], xn[kGT_X], ylo[kGRows], yn[kGRows];
+    __shared__ int s_x[3];  // ox0, cols, columns fit
+    const int tid = threadIdx.x, nt = kGT_Y * kGT_X;
+    const int sy = tid / kGT_X, sx = tid - sy * kGT_X;
+    // The ranges and weights depend on the geometry only, not on the map: a CTA keeps ONE strip position
+    // (column tile, row chunk) and walks over the maps, so the set-up below runs once per CTA.
+    const int n_classes = chunks_y * tiles_x;
+    const int cls = blockIdx.x % n_classes, m_first = blockIdx.x / n_classes, m_step = max(1, (int)gridDim.x / n_classes);
+    if (blockIdx.x >= (unsigned)(m_step * n_classes)) return;  // (grid is a multiple of the classes: never taken)
+    const int tx = cls % tiles_x, cy = cls / tiles_x;
+    const int sx0 = tx * kGT_X, row0 = cy * kGRows, n_rows = min(kGRows, a.Hs - row0);
+    {
+        if (tid < kGT_X) {
+            int lo = 0, hi = -1;
+            if (sx0 + tid < a.Ws) post_out_range(a.s2x, a.rw, a.s1x, a.Ws, a.ow, sx0 + tid, lo, hi);
+            xlo[tid] = lo; xn[tid] = hi >= lo ? hi - lo + 1 : 0;
+        }
+        if (tid < n_rows) {
+            int lo = 0, hi = -1;
+            post_out_range(a.s2y, a.rh, a.s1y, a.Hs, a.oh, row0 + tid, lo, hi);
+            ylo[tid] = lo; yn[tid] = hi >= lo ? hi - lo + 1 : 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int x0 = 1 << 30, x1 = -1, kmax = 0;
+            for (int i = 0; i < kGT_X; ++i) if (xn[i]) { x0 = min(x0, xlo[i]); x1 = max(x1, xlo[i] + xn[i] - 1); kmax = max(kmax, xn[i]); }
+            const int cols = x1 >= x0 ? x1 - x0 + 1 : 0;
+            s_x[0] = cols ? x0 : 0; s_x[1] = cols; s_x[2] = cols <= kGWC && kmax <= kGK;
+        }
+        for (int i = tid; i < kGT_X * kGK; i += nt) {
+            const int c = i / kGK, j = i - c * kGK;
+            wx[c][j] = j < xn[c] ? post_axis_weight(a.s2x, a.rw, a.s1x, a.Ws, xlo[c] + j, sx0 + c) : 0.f;
+        }
+        for (int i = tid; i < n_rows * kGK; i += nt) {
+            const int r = i / kGK, j = i - r * kGK;
+            wy[r][j] = j < yn[r] ? post_axis_weight(a.s2y, a.rh, a.s1y, a.Hs, ylo[r] + j, row0 + r) : 0.f;
+        }
+        __syncthreads();
+    }
+    for (long long m = m_first; m < a.n_maps; m += m_step) {
+        const float* g = a.gout + m * (long long)a.oh * a.ow;
+        float* gin = a.gin + m * (long long)a.Hs * a.Ws;
+        const int ox0 = s_x[0], cols = s_x[1];
+        for (int r0 = 0; r0 < n_rows; r0 += kGTileRows) {
+            // the tile's rows of grad_out: ranges are monotone in the source row
+            const int r_last = min(n_rows, r0 + kGTileRows) - 1;
+            int oy0 = 1 << 30, oy1 = -1, kmax = 0;
+            for (int i = r0; i <= r_last; ++i) if (yn[i]) { oy0 = min(oy0, ylo[i]); oy1 = max(oy1, ylo[i] + yn[i] - 1); kmax = max(kmax, yn[i]); }
+            const int rows = oy1 >= oy0 ? oy1 - oy0 + 1 : 0;
+            const bool fits = s_x[2] && rows <= kGWR && kmax <= kGK;  // block-uniform
+            float acc[2] = {0.f, 0.f};
+            if (fits) {
+                for (int r = tid >> 5; r < rows; r += nt >> 5)  // a warp per window row: coalesced, no divisions
+                    for (int c = tid & 31; c < cols; c += 32) gw[r][c] = __ldg(g + (long long)(oy0 + r) * a.ow + ox0 + c);
+                __syncthreads();
+                for (int i = tid; i < rows * kGT_X; i += nt) {  // along x: T[row][source column]
+                    const int r = i / kGT_X, c = i - r * kGT_X;
+                    float t = 0.f;
+                    const int base = xlo[c] - ox0, n = xn[c];
+                    for (int j = 0; j < n; ++j) t += wx[c][j] * gw[r][base + j];
+                    Tt[r][c] = t;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int my = r0 + sy + h * kGT_Y;
+                    if (my <= r_last) {
+                        const int base = ylo[my] - oy0, n = yn[my];
+                        for (int j = 0; j < n; ++j) acc[h] += wy[my][j] * Tt[base + j][sx];
+                    }
+                }
+                __syncthreads();  // Tt / gw are rewritten by the next tile
+            } else {  // window or tap count beyond the staging buffers: straight from global
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int my = r0 + sy + h * kGT_Y;
+                    if (my > r_last || sx0 + sx >= a.Ws) continue;
+                    for (int jy = 0; jy < yn[my]; ++jy) {
+                        const int oy = ylo[my] + jy;
+                        const float wv = post_axis_weight(a.s2y, a.rh, a.s1y, a.Hs, oy, row0 + my);
+                        if (wv == 0.f) continue;
+                        float t = 0.f;
+                        for (int jx = 0; jx < xn[sx]; ++jx) {
+                            const int ox = xlo[sx] + jx;
+                            t += post_axis_weight(a.s2x, a.rw, a.s1x, a.Ws, ox, sx0 + sx) * __ldg(g + (long long)oy * a.ow + ox);
+                        }
+                        acc[h] += wv * t;
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int my = r0 + sy + h * kGT_Y;
+                if (my <= r_last && sx0 + sx < a.Ws) gin[(long long)(row0 + my) * a.Ws + sx0 + sx] = acc[h];
+            }
+        }
+    }
+}
+
 }  // namespace tl

@@ -671,6 +671,20 @@ int tl_postprocess_backward(const float* grad_out, int n_maps, int Hs, int Ws, i
     if (reinterpret_cast<uintptr_t>(grad_in) & 15) return fail(TL_ERR_ARG, "grad_in must be 16-byte aligned");
     a.gout = grad_out; a.gin = grad_in;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // taps per source pixel and axis: 2 * (out / mid) * (T / src) + 3.  Few (the reference down-samples to the
+    // original size): gather kernel, every source pixel written once.  Many (strong up-sampling): scatter kernel.
+    const double ky = 2.0 * oh * T / ((double)Hs * rh) + 3.0, kx = 2.0 * ow * T / ((double)Ws * rw) + 3.0;
+    if (ky <= tl::kGK && kx <= tl::kGK) {
+        const int gcy = (Hs + tl::kGRows - 1) / tl::kGRows, gtx = (Ws + tl::kGT_X - 1) / tl::kGT_X;
+        // a CTA keeps one strip position (gcy * gtx of them) and walks over maps: grid = positions x map lanes
+        const int classes = gcy * gtx;
+        int lanes = (148 * 10 + classes - 1) / classes;
+        if (lanes > n_maps) lanes = n_maps;
+        if (lanes < 1) lanes = 1;
+        tl::postprocess_bwd_gather_kernel<<<classes * lanes, tl::kGT_Y * tl::kGT_X, 0, st>>>(a, gcy, gtx);
+        TL_CUDA(cudaGetLastError());
+        return TL_OK;
+    }
     const long long n = (long long)n_maps * Hs * Ws;
     tl::zero_fill_kernel<<<grid_for(n >> 2, 256), 256, 0, st>>>(grad_in, n);
     TL_CUDA(cudaGetLastError());

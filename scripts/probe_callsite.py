@@ -75,6 +75,19 @@ res["torch_postprocess_bwd_ms"] = timeit(lambda: torch.autograd.grad(yb, pb, gm,
 del yb
 res["postprocess_fwd_GBps"] = (B * C * (256 * 256 + H * W) * 4) / (res["postprocess_fwd_ms"] * 1e-3) / 1e9   # read source + write output
 res["postprocess_bwd_GBps"] = (B * C * (256 * 256 + H * W) * 4) / (res["postprocess_bwd_ms"] * 1e-3) / 1e9   # read grad_out + write grad_in
+# ---- F2: DiceCELoss(sigmoid=True) on the post-processed masks (training_utils.py:62), fused kernel vs the PyTorch ops
+from oracle.dice_ce_oracle import dice_ce   # (a measurement script may use the oracle as the PyTorch-ops arm)
+lx = torch.randn((B, C, H, W), device="cuda", generator=gen).requires_grad_(True)
+tg = (torch.rand((B, C, H, W), device="cuda", generator=gen) < 0.3).float()
+def dc_fused():
+    lx.grad = None
+    tlb.dice_ce_loss(lx, tg).backward()
+def dc_torch():
+    lx.grad = None
+    dice_ce(lx, tg).backward()
+res["dice_ce_fused_fwd_bwd_ms"] = timeit(dc_fused)
+res["dice_ce_torch_fwd_bwd_ms"] = timeit(dc_torch)
+res["dice_ce_fused_GBps"] = (B * C * H * W * 4 * 5) / (res["dice_ce_fused_fwd_bwd_ms"] * 1e-3) / 1e9   # fwd reads 2, bwd reads 2 + writes 1
 bytes_grad = B * C * H * W * 4
 res["resample_bwd_write_GBps"] = bytes_grad / (res["resample_bwd_ms"] * 1e-3) / 1e9
 res["dense_grad_bytes"] = bytes_grad
