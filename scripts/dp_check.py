@@ -52,7 +52,7 @@ def _time(fn, n=5, warm=2):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t)
 
-Bl, Nmax = int(os.environ.get("DP_LOCAL_BATCH", "8")), 14
+Bl, Nmax = int(os.environ.get("DP_LOCAL_BATCH", "32")), 14  # C3: bs 256 over 8 GPUs
 g = torch.Generator().manual_seed(100 + rank)
 big = {"pixel_values": torch.randn((Bl, 3, 1024, 1024), generator=g).cuda(),
        "input_boxes": (torch.rand((Bl, Nmax, 4), generator=g) * 500 + torch.tensor([0.0, 0, 400, 400])).cuda(),
@@ -63,6 +63,23 @@ optt = torch.optim.Adam(mt.mask_decoder.parameters(), lr=1e-3)
 dec = list(mt.mask_decoder.parameters())
 st2 = {}
 ms_step = _time(lambda: training_step(_SamWithSizes(mt), big, gt_big, optt, None, global_batch=Bl * world, decoder_params=dec, stats=st2))
+# the part of the step this repo owns: post-processing + DiceCE + topological loss, forward and backward to the decoder output
+import dilabhelmholtzoct_b200 as tlb
+low = torch.randn((Bl, Nmax, 256, 256), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5 + rank)).requires_grad_(True)
+def loss_side():
+    low.grad = None
+    masks = tlb.postprocess_masks(low, (992, 1024), (496, 512))
+    (tlb.dice_ce_loss(masks, gt_big) + tlb.topo_loss_from_logits(masks, gt_big, 0.1, feat_d=1, interp=50)).backward()
+def loss_side_torch():
+    low.grad = None
+    m_ = F.interpolate(low, (1024, 1024), mode="bilinear", align_corners=False)[..., :992, :1024]
+    m_ = F.interpolate(m_, (496, 512), mode="bilinear", align_corners=False)
+    s_ = torch.sigmoid(m_)
+    ax = (2, 3)
+    dice = (1 - (2 * (s_ * gt_big).sum(ax) + 1e-5) / (gt_big.sum(ax) + s_.sum(ax) + 1e-5)).mean()
+    (dice + F.cross_entropy(m_, gt_big) + tlb.topo_loss(s_, gt_big, 0.1, feat_d=1, interp=50)).backward()
+ms_loss_side = _time(loss_side, n=10, warm=3)
+ms_loss_side_torch = _time(loss_side_torch, n=10, warm=3)
 from dilabhelmholtzoct_b200.parallel import allreduce_gradients
 ms_ar = _time(lambda: allreduce_gradients(dec), n=20, warm=3)
 out = {"rank": rank, "world": world, "loss_dp": float(loss_dp), "loss_single": float(loss_1),
@@ -70,9 +87,12 @@ out = {"rank": rank, "world": world, "loss_dp": float(loss_dp), "loss_single": f
        "step": {"local_batch": Bl, "prompts": Nmax, "original_size": [496, 512], "ms_per_step_max_over_ranks": ms_step,
                 "decoder_params": sum(p.numel() for p in dec), "grad_allreduce_bytes": st2.get("grad_allreduce_bytes"),
                 "grad_allreduce_ms": ms_ar,
+                "loss_side_ms": ms_loss_side, "loss_side_pytorch_ops_ms": ms_loss_side_torch,
                 "grad_allreduce_GBps": (st2.get("grad_allreduce_bytes") or 0) / max(ms_ar, 1e-9) / 1e6,
                 "note": "tiny random vision encoder + the real-size SAM mask decoder (no weights offline); "
-                        "postprocess_masks + dice_ce_loss + fused topo loss (interp=50) + SUM all-reduce of decoder gradients"}}
+                        "postprocess_masks + dice_ce_loss + fused topo loss (interp=50) + SUM all-reduce of decoder gradients; "
+                        "loss_side = everything between the decoder output and its gradient (this repo's kernels vs PyTorch ops "
+                        "around the CUDA topological loss); the step time itself is dominated by the stand-in vision encoder"}}
 gathered = [None] * world
 dist.all_gather_object(gathered, out)
 if rank == 0:
