@@ -68,15 +68,15 @@ __global__ void __launch_bounds__(kMatchThreads) match_kernel(MatchArgs A) {
     __shared__ int s_k;
     // maps with a non-empty ground-truth diagram cost 10-100x the others: hand the maps out dynamically
     const int n_work = A.list ? (int)*A.n_list : A.n_diag;
-    for (int k = blockIdx.x;; k += gridDim.x) {
+    for (int w = blockIdx.x;; w += gridDim.x) {  // w: position in the work list, k: the diagram it names
         if (A.counter) {
             __syncthreads();
             if (tid == 0) s_k = (int)atomicAdd(A.counter, 1u);
             __syncthreads();
-            k = s_k;
+            w = s_k;
         }
-        if (k >= n_work) break;
-        if (A.list) k = A.list[k];
+        if (w >= n_work) break;
+        const int k = A.list ? A.list[w] : w;
         const int n = A.d1.rows(k), m = A.d2.rows(k);
         const char* r1 = A.d1.first(k);
         const char* r2 = A.d2.first(k);

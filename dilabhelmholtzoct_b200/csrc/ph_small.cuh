@@ -514,6 +514,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
     __shared__ double s_red[kPhThreads / 32];
     __shared__ unsigned long long s_base;
     const PhArgs& A = S.base;
+    const uint64_t l2_keep = l2_policy_evict_last();
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int H = A.H, W = A.W, N = H * W;
     uint16_t* par = reinterpret_cast<uint16_t*>(smem);
@@ -732,21 +733,12 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
                 for (int t = 0; t < trips; ++t) {
                     const int x = wbeg + t * 128 + lane * 4;  // band-local id of the quad
                     unsigned defer = 0u;
-#ifdef TL_PREFETCH_L1
-                    if (lane < 12 && t + 1 < trips) {  // next trip's three half rows (4 lines each) into L1
-                        const int xn = wbeg + (t + 1) * 128 + (lane & 3) * 32;
-                        if (xn < wend) {
-                            const int rn = (int)divW.div((uint32_t)xn) + (lane >> 2) - 1;
-                            if (rn >= 0 && rn < H) asm volatile("prefetch.global.L1 [%0];" :: "l"(f + (size_t)rn * W + c0 + (xn - (rn - (lane >> 2) + 1) * bw)));
-                        }
-                    }
-#endif
                     if (x < wend) {
                         const int r = (int)divW.div((uint32_t)x), cl = x - r * bw, c = c0 + cl;
                         const float* q = f + r * W + c;
-                        const float4 M = __ldg(reinterpret_cast<const float4*>(q));
-                        const float4 U = r > 0 ? __ldg(reinterpret_cast<const float4*>(q - W)) : M;
-                        const float4 D = r < H - 1 ? __ldg(reinterpret_cast<const float4*>(q + W)) : M;
+                        const float4 M = ldg_f4_keep(reinterpret_cast<const float4*>(q), l2_keep);
+                        const float4 U = r > 0 ? ldg_f4_keep(reinterpret_cast<const float4*>(q - W), l2_keep) : M;
+                        const float4 D = r < H - 1 ? ldg_f4_keep(reinterpret_cast<const float4*>(q + W), l2_keep) : M;
                         const float L = c > 0 ? __ldg(q - 1) : 0.f;
                         const float R = c + 4 < W ? __ldg(q + 4) : 0.f;
                         vlo = fminf(vlo, fminf(fminf(M.x, M.y), fminf(M.z, M.w)));
@@ -938,15 +930,6 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
                 const int x = wbeg + t * 128 + lane * 4;
                 const bool valid = x < wend;
                 unsigned flags = 0u;
-#ifdef TL_PREFETCH_L1
-                if (lane < 8 && t + 1 < trips) {  // next trip's two half rows (own row, row above) into L1
-                    const int xn = wbeg + (t + 1) * 128 + (lane & 3) * 32;
-                    if (xn < wend) {
-                        const int r0 = (int)divW.div((uint32_t)xn), rn = r0 - (lane >> 2);
-                        if (rn >= 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(f + (size_t)rn * W + c0 + (xn - r0 * bw)));
-                    }
-                }
-#endif
                 uint32_t lab[5] = {0u, 0u, 0u, 0u, 0u}, ulab[4] = {0u, 0u, 0u, 0u};  // lab[0]: left of the quad
                 float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, u[4] = {0.f, 0.f, 0.f, 0.f};
                 int r = 0, c = 0, cl = 0;
@@ -964,11 +947,11 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
                         ulab[0] = llab(wu.x & 0xFFFFu); ulab[1] = llab(wu.x >> 16); ulab[2] = llab(wu.y & 0xFFFFu); ulab[3] = llab(wu.y >> 16);
                     }
                     const float* q = f + r * W + c;
-                    const float4 M = __ldg(reinterpret_cast<const float4*>(q));
+                    const float4 M = ldg_f4_keep(reinterpret_cast<const float4*>(q), l2_keep);
                     m[1] = M.x; m[2] = M.y; m[3] = M.z; m[4] = M.w;
                     if (c > 0) m[0] = __ldg(q - 1);
                     if (r > 0) {
-                        const float4 U = __ldg(reinterpret_cast<const float4*>(q - W));
+                        const float4 U = ldg_f4_keep(reinterpret_cast<const float4*>(q - W), l2_keep);
                         u[0] = U.x; u[1] = U.y; u[2] = U.z; u[3] = U.w;
                     }
 #pragma unroll
@@ -1435,7 +1418,11 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
                     const int j = j0 + u * nt;
                     if (j < avail) {
                         rec4[u].tb = rec4[u].td = __int_as_float(0x7FC00000);
-                        out[j] = rec4[u];
+                        {   // written once, read by later kernels only: stream past L2
+                            const uint2* rw = reinterpret_cast<const uint2*>(&rec4[u]);
+                            uint2* ow = reinterpret_cast<uint2*>(out + j);
+                            __stcs(ow, rw[0]); __stcs(ow + 1, rw[1]); __stcs(ow + 2, rw[2]);
+                        }
                         if (skeys) skeys[j] = sk4[u];
                         dacc += (double)cost_diag(rec4[u].b, rec4[u].d, A.ps.q);
                     }

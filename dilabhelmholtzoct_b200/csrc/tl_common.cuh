@@ -96,6 +96,20 @@ __device__ __forceinline__ float unmono32(uint32_t m) {
     return __uint_as_float((m & 0x80000000u) ? (m & 0x7FFFFFFFu) : ~m);
 }
 
+// L2 residency hints (per instruction, no device-wide state): the map a CTA works on is read three times (level 0,
+// compaction, emission) and should stay in L2 between them; the pair records are written once and read by later
+// kernels only, so they stream past it.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg_f4_keep(const float4* ptr, uint64_t policy) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(policy));
+    return v;
+}
+
 __device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t* p) {
     return __ldcg(reinterpret_cast<const unsigned long long*>(p));
 }

@@ -13,7 +13,7 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
-B = 2 * world
+B = int(os.environ.get("DP_IMAGES_PER_RANK", "2")) * world
 inputs, gt = _batch(B=B, N=3, size=64)
 base = _tiny_sam().cuda()
 # sharded step

@@ -535,3 +535,13 @@ def test_c5_scale_one_full_image():
     assert abs(loss - want) <= REL * abs(want), (loss, want)
     assert np.array_equal(grad != 0, wgrad != 0)
     assert np.abs(grad - wgrad).max() <= REL * np.abs(wgrad).max()
+
+
+def test_loss_many_maps_with_two_large_diagrams():
+    """More maps with two large diagrams (> 8 points each) than the general matching kernel has scratch slots (16):
+    every one of them must be matched exactly once (a loop-index bug once skipped / repeated some)."""
+    rng = torch.Generator().manual_seed(9)
+    pred = torch.rand((8, 6, 40, 40), generator=rng)
+    truth = torch.nn.functional.avg_pool2d(torch.rand((8, 6, 80, 80), generator=rng), 2)
+    for _ in range(2):
+        _check_loss(pred, truth, 0.1, 1)
