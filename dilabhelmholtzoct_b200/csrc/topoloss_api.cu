@@ -89,7 +89,8 @@ constexpr int kPhSlots = 296;      // CTAs of the global-memory persistence kern
 constexpr int kSmallSlotsMax = 160;  // per-CTA scratch slots of ph_small_kernel: one 1024-thread CTA per SM
 constexpr int kSortSlots = 64;
 constexpr int kMatchSlots = 296;   // tl_wasserstein
-constexpr int kHeavySlots = 16;    // maps whose two diagrams both exceed kSmallR points (rare)
+constexpr int kHeavySlotsMin = 16;  // maps whose two diagrams both exceed kSmallR points (rare with segmentation ground truth);
+constexpr size_t kHeavyBytes = 32u << 20;  // scratch budget: small maps get up to kMatchSlots slots, 256 x 256 maps ~19
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -147,6 +148,7 @@ struct ScratchLayout {
     size_t T, t_stride;
     size_t skeys, key_tmp, idx_a, idx_b, rec_tmp;
     size_t v, minv, u, way, pcol, used, stride_c, stride_r;
+    int heavy_slots;
     size_t total;
 };
 ScratchLayout make_scratch(int H, int W, int dim, bool with_sort, unsigned long long arena_records) {
@@ -194,12 +196,14 @@ ScratchLayout make_scratch(int H, int W, int dim, bool with_sort, unsigned long 
     } else {
         L.stride_c = align_up((size_t)2 * L.cap + 2, 32);
         L.stride_r = align_up((size_t)L.cap + 2, 32);
-        L.v = take(sizeof(double) * L.stride_c * kHeavySlots);
-        L.minv = take(sizeof(double) * L.stride_c * kHeavySlots);
-        L.u = take(sizeof(double) * L.stride_r * kHeavySlots);
-        L.way = take(sizeof(int32_t) * L.stride_c * kHeavySlots);
-        L.pcol = take(sizeof(int32_t) * L.stride_c * kHeavySlots);
-        L.used = take(L.stride_c * kHeavySlots);
+        size_t hs = kHeavyBytes / (29 * L.stride_c);  // 8 + 8 + 4 + 4 + 1 bytes per column, 8 per row (<= half the columns)
+        L.heavy_slots = (int)(hs < (size_t)kHeavySlotsMin ? (size_t)kHeavySlotsMin : hs > (size_t)kMatchSlots ? (size_t)kMatchSlots : hs);
+        L.v = take(sizeof(double) * L.stride_c * L.heavy_slots);
+        L.minv = take(sizeof(double) * L.stride_c * L.heavy_slots);
+        L.u = take(sizeof(double) * L.stride_r * L.heavy_slots);
+        L.way = take(sizeof(int32_t) * L.stride_c * L.heavy_slots);
+        L.pcol = take(sizeof(int32_t) * L.stride_c * L.heavy_slots);
+        L.used = take(L.stride_c * L.heavy_slots);
     }
     L.total = o > 0 ? o : 256;
     return L;
@@ -431,7 +435,7 @@ int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W
         m.list = mf.heavy; m.n_list = mf.n_heavy;
         fill_match_scratch(m, scratch, L.v, L.minv, L.u, L.way, L.pcol, L.used, L.stride_c, L.stride_r);
         m.counter = nullptr;
-        tl::match_kernel<<<M < kHeavySlots ? M : kHeavySlots, tl::kMatchThreads, 0, st>>>(m);
+        tl::match_kernel<<<M < L.heavy_slots ? M : L.heavy_slots, tl::kMatchThreads, 0, st>>>(m);
         TL_CUDA(cudaGetLastError());
     }
     tm.mark(3, st);

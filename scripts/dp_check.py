@@ -57,7 +57,12 @@ g = torch.Generator().manual_seed(100 + rank)
 big = {"pixel_values": torch.randn((Bl, 3, 1024, 1024), generator=g).cuda(),
        "input_boxes": (torch.rand((Bl, Nmax, 4), generator=g) * 500 + torch.tensor([0.0, 0, 400, 400])).cuda(),
        "reshaped_input_sizes": torch.tensor([[992, 1024]] * Bl).cuda(), "original_sizes": torch.tensor([[496, 512]] * Bl).cuda()}
-gt_big = (torch.rand((Bl, Nmax, 496, 512), generator=g) < 0.3).float().cuda()
+# ground truth: OCT-like layers + blobs (dilabhelmholtzoct_b200.synthetic), one component mask per prompt -- NOT iid noise,
+# whose diagrams (hundreds of points on both sides) would make the exact assignment, not the step, the thing measured
+from dilabhelmholtzoct_b200.synthetic import make_labels
+_gen = torch.Generator().manual_seed(300 + rank)
+_lab = make_labels(Bl, 496, 512, _gen, n_classes=Nmax)
+gt_big = torch.nn.functional.one_hot(_lab, Nmax).permute(0, 3, 1, 2).float().contiguous().cuda()
 mt = copy.deepcopy(base)
 optt = torch.optim.Adam(mt.mask_decoder.parameters(), lr=1e-3)
 dec = list(mt.mask_decoder.parameters())
@@ -65,7 +70,8 @@ st2 = {}
 ms_step = _time(lambda: training_step(_SamWithSizes(mt), big, gt_big, optt, None, global_batch=Bl * world, decoder_params=dec, stats=st2))
 # the part of the step this repo owns: post-processing + DiceCE + topological loss, forward and backward to the decoder output
 import dilabhelmholtzoct_b200 as tlb
-low = torch.randn((Bl, Nmax, 256, 256), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5 + rank)).requires_grad_(True)
+_t256 = torch.nn.functional.interpolate(gt_big, (256, 256), mode="bilinear", align_corners=False)
+low = (4.0 * (2.0 * _t256 - 1.0) + 0.5 * torch.randn((Bl, Nmax, 256, 256), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5 + rank))).requires_grad_(True)
 def loss_side():
     low.grad = None
     masks = tlb.postprocess_masks(low, (992, 1024), (496, 512))
