@@ -962,6 +962,26 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
                         if (c + k == W - 1 && own != 0u) flags |= 4u << (4 * k);
                         if (r == H - 1 && own != 0u) flags |= 8u << (4 * k);
                     }
+                    // Same-pair duplicates that are visible in registers: of two crossing edges that join the SAME two
+                    // basins only the earlier one (larger value, then larger position) can be a tree edge.
+                    //  (i)  a pixel's left and top edge lead into the same basin;
+                    //  (ii) the top edges of two neighbouring pixels of one basin lead into the same basin.
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned lf = 1u << (4 * k), tp = 2u << (4 * k);
+                        if ((flags & lf) && (flags & tp) && lab[k] == ulab[k]) {
+                            const float vl = c + k == 0 ? m[k + 1] : fminf(m[k], m[k + 1]), vt = r == 0 ? m[k + 1] : fminf(u[k], m[k + 1]);
+                            flags &= vt > vl ? ~lf : ~tp;  // on a tie the v-edge (larger position) is the earlier one
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const unsigned t0 = 2u << (4 * k), t1 = 2u << (4 * (k + 1));
+                        if ((flags & t0) && (flags & t1) && lab[k + 1] == lab[k + 2] && ulab[k] == ulab[k + 1]) {
+                            const float v0 = r == 0 ? m[k + 1] : fminf(u[k], m[k + 1]), v1 = r == 0 ? m[k + 2] : fminf(u[k + 1], m[k + 2]);
+                            flags &= v0 > v1 ? ~t1 : ~t0;  // on a tie the right-hand edge (larger position) is the earlier one
+                        }
+                    }
                     if (xband) {  // always crossing: level-0 links never leave a band
                         const int ix = atomicAdd(&s_nx, 1);
                         const uint32_t posg = (uint32_t)(r * GW + W + c);
