@@ -52,22 +52,62 @@ def _time(fn, n=5, warm=2):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t)
 
-Bl, Nmax = int(os.environ.get("DP_LOCAL_BATCH", "32")), 14  # C3: bs 256 over 8 GPUs
+# Model of the timed step (DP_MODEL): "tiny" = stand-in vision encoder + the real mask decoder (default, cheap);
+# "vit_b" = transformers' SamModel(SamConfig()) = SAM ViT-B (93.7 M parameters, BASELINE configs[2], random init: no weights
+# offline); "vit_l" = SAM ViT-L (hidden 1024, 24 layers, 16 heads, global attention at 5/11/17/23; configs[3]).
+# DP_PROMPT = boxes | points (training.py --prompt).  DP_LOCAL_BATCH: images per GPU (C3: 32, C4 at 8 GPUs: 64).
+model_kind, prompt = os.environ.get("DP_MODEL", "tiny"), os.environ.get("DP_PROMPT", "boxes")
+Bl, Nmax = int(os.environ.get("DP_LOCAL_BATCH", "32")), 14
+n_time, n_warm = (5, 2) if model_kind == "tiny" else (3, 1)
+
+
+def _big_model():
+    if model_kind == "tiny":
+        return copy.deepcopy(base)
+    from transformers import SamConfig, SamModel
+    from transformers.models.sam.configuration_sam import SamVisionConfig
+    torch.manual_seed(0)
+    cfg = SamConfig() if model_kind == "vit_b" else SamConfig(vision_config=SamVisionConfig(
+        hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, global_attn_indexes=[5, 11, 17, 23], mlp_dim=4096))
+    m_ = SamModel(cfg)
+    for name, p_ in m_.named_parameters():  # prepare_model, training_utils.py:277-279
+        if name.startswith("vision_encoder") or name.startswith("prompt_encoder"):
+            p_.requires_grad_(False)
+    return m_.cuda()
+
+
+class _Sam(torch.nn.Module):  # training_step calls model(**inputs): drop the two size entries the HF model does not take
+    def __init__(self, sam):
+        super().__init__()
+        self.sam = sam
+
+    def forward(self, pixel_values, input_boxes=None, input_points=None, reshaped_input_sizes=None, original_sizes=None, multimask_output=False):
+        if input_points is not None:
+            return self.sam(pixel_values=pixel_values, input_points=input_points, multimask_output=multimask_output)
+        return self.sam(pixel_values=pixel_values, input_boxes=input_boxes, multimask_output=multimask_output)
+
+
 g = torch.Generator().manual_seed(100 + rank)
 big = {"pixel_values": torch.randn((Bl, 3, 1024, 1024), generator=g).cuda(),
-       "input_boxes": (torch.rand((Bl, Nmax, 4), generator=g) * 500 + torch.tensor([0.0, 0, 400, 400])).cuda(),
        "reshaped_input_sizes": torch.tensor([[992, 1024]] * Bl).cuda(), "original_sizes": torch.tensor([[496, 512]] * Bl).cuda()}
+if prompt == "points":
+    big["input_points"] = (torch.rand((Bl, Nmax, 1, 2), generator=g) * 900 + 50).cuda()
+else:
+    big["input_boxes"] = (torch.rand((Bl, Nmax, 4), generator=g) * 500 + torch.tensor([0.0, 0, 400, 400])).cuda()
 # ground truth: OCT-like layers + blobs (dilabhelmholtzoct_b200.synthetic), one component mask per prompt -- NOT iid noise,
 # whose diagrams (hundreds of points on both sides) would make the exact assignment, not the step, the thing measured
 from dilabhelmholtzoct_b200.synthetic import make_labels
 _gen = torch.Generator().manual_seed(300 + rank)
 _lab = make_labels(Bl, 496, 512, _gen, n_classes=Nmax)
 gt_big = torch.nn.functional.one_hot(_lab, Nmax).permute(0, 3, 1, 2).float().contiguous().cuda()
-mt = copy.deepcopy(base)
+mt = _big_model()
 optt = torch.optim.Adam(mt.mask_decoder.parameters(), lr=1e-3)
 dec = list(mt.mask_decoder.parameters())
 st2 = {}
-ms_step = _time(lambda: training_step(_SamWithSizes(mt), big, gt_big, optt, None, global_batch=Bl * world, decoder_params=dec, stats=st2))
+step_fn = lambda: training_step(_Sam(mt), big, gt_big, optt, None, global_batch=Bl * world, decoder_params=dec, stats=st2)
+ms_step = _time(step_fn, n=n_time, warm=n_warm)
+ms_step_no_topo = _time(lambda: training_step(_Sam(mt), big, gt_big, optt, None, topological=False, global_batch=Bl * world, decoder_params=dec),
+                        n=n_time, warm=1)
 # the part of the step this repo owns: post-processing + DiceCE + topological loss, forward and backward to the decoder output
 import dilabhelmholtzoct_b200 as tlb
 _t256 = torch.nn.functional.interpolate(gt_big, (256, 256), mode="bilinear", align_corners=False)
@@ -90,15 +130,18 @@ from dilabhelmholtzoct_b200.parallel import allreduce_gradients
 ms_ar = _time(lambda: allreduce_gradients(dec), n=20, warm=3)
 out = {"rank": rank, "world": world, "loss_dp": float(loss_dp), "loss_single": float(loss_1),
        "rel_update_err": (num / max(den, 1e-30)) ** 0.5,
-       "step": {"local_batch": Bl, "prompts": Nmax, "original_size": [496, 512], "ms_per_step_max_over_ranks": ms_step,
+       "step": {"model": model_kind, "prompt": prompt, "model_params": sum(p.numel() for p in mt.parameters()),
+                "local_batch": Bl, "global_batch": Bl * world, "prompts": Nmax, "original_size": [496, 512],
+                "ms_per_step_max_over_ranks": ms_step, "ms_per_step_without_topo": ms_step_no_topo,
+                "images_per_s": Bl * world / (ms_step * 1e-3),
                 "decoder_params": sum(p.numel() for p in dec), "grad_allreduce_bytes": st2.get("grad_allreduce_bytes"),
                 "grad_allreduce_ms": ms_ar,
                 "loss_side_ms": ms_loss_side, "loss_side_pytorch_ops_ms": ms_loss_side_torch,
                 "grad_allreduce_GBps": (st2.get("grad_allreduce_bytes") or 0) / max(ms_ar, 1e-9) / 1e6,
-                "note": "tiny random vision encoder + the real-size SAM mask decoder (no weights offline); "
+                "note": "DP_MODEL=tiny: tiny random vision encoder + the real-size SAM mask decoder; vit_b / vit_l: transformers SamModel, random init (no weights offline); "
                         "postprocess_masks + dice_ce_loss + fused topo loss (interp=50) + SUM all-reduce of decoder gradients; "
                         "loss_side = everything between the decoder output and its gradient (this repo's kernels vs PyTorch ops "
-                        "around the CUDA topological loss); the step time itself is dominated by the stand-in vision encoder"}}
+                        "around the CUDA topological loss); the step time itself is dominated by the (frozen) vision encoder's forward pass"}}
 gathered = [None] * world
 dist.all_gather_object(gathered, out)
 if rank == 0:

@@ -1,5 +1,5 @@
-"""Round-2 probe: phase cycles of the persistence kernel on the headline maps for a few runtime variants
-(TL_BV_ROUNDS, TL_NO_BINARY are read per call), then stage times of the whole step."""
+"""Round-2 probe: phase cycles of the persistence kernel on the headline maps (prediction, iid noise, ground truth with and
+without the two-valued path, H0); the library is chosen with TL_PROBE_LIB (A/B of build variants: scripts/gpu_ab.sh)."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
