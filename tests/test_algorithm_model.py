@@ -70,7 +70,7 @@ def _kruskal(nkey, edges):
     return out
 
 
-def _model(nkey, edges, val, rng, level0, boruvka=0):
+def _model(nkey, edges, val, rng, level0, boruvka=0, dedup=False, bands=0):
     n = len(nkey)
     T = [(INF, x) for x in range(n)]  # (edge at which x dies, elder target)
     if level0:
@@ -137,7 +137,28 @@ def _model(nkey, edges, val, rng, level0, boruvka=0):
                 return x
             es = [(s, live(a), live(b)) for s, a, b in es]
             es = [e for e in es if e[1] != e[2]]
+    def root0_(x):
+        while T[x][0] == -INF:
+            x = T[x][1]
+        return x
+    if dedup:
+        # csrc/ph_small.cuh, compaction: of several crossing edges that join the SAME two basins only the earliest can be
+        # a tree edge; the kernel drops the later ones it can see in registers -- here ALL of them (the strongest form)
+        best = {}
+        for s, a, b in es:
+            pa, pb = root0_(a), root0_(b)
+            if pa == pb:
+                continue
+            k = (min(pa, pb), max(pa, pb))
+            if k not in best or s < best[k][0]:
+                best[k] = (s, a, b)
+        es = list(best.values())
     rng.shuffle(es)  # ANY order
+    if bands:
+        # multi-band maps: every band's own edges first (band by band, as the kernel merges them on a band-local table
+        # whose entries then move to the global table), the edges across band borders last
+        band_of = lambda x: min(bands - 1, x * bands // len(nkey))
+        es.sort(key=lambda e: band_of(e[1]) if band_of(e[1]) == band_of(e[2]) else bands)
     for s, x, y in es:
         while True:
             x, y = rep(x, s), rep(y, s)
@@ -169,6 +190,9 @@ def test_triplet_merge_equals_kruskal_for_any_edge_order(seed):
             for level0 in (True, False):
                 got = sorted((y, s) for y, s in _model(nkey, edges, val, rng, level0) if val(s) != val(nkey[y]))
                 assert got == want, (dim, level0, f.tolist())
+            for kw in (dict(dedup=True), dict(bands=3), dict(dedup=True, bands=2)):  # duplicate-edge filter; band-by-band order
+                got = sorted((y, s) for y, s in _model(nkey, edges, val, rng, True, **kw) if val(s) != val(nkey[y]))
+                assert got == want, (dim, kw, f.tolist())
             for rounds in (1, 2, 4, 50):  # contraction rounds first, lock-free merge for the rest
                 got = sorted((y, s) for y, s in _model(nkey, edges, val, rng, True, boruvka=rounds) if val(s) != val(nkey[y]))
                 assert got == want, (dim, "boruvka", rounds, f.tolist())
