@@ -13,6 +13,7 @@
 #pragma once
 #include <math.h>
 #include "tl_common.cuh"
+#include "grad_kernel.cuh"
 #include "match_small.cuh"
 
 namespace tl {
@@ -190,12 +191,10 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs A) {
     const int Bg = A.B_global > 0 ? A.B_global : A.B;
     double acc = 0.0, reg = 0.0;
     for (int b = tid; b < A.B; b += blockDim.x) {
-        float S = 0.f;  // total_cost += emd2(...) runs in fp32 in the reference
-        for (int c = 0; c < A.C; ++c) S += (float)A.cost[b * A.C + c];
+        float S;  // total_cost += emd2(...) runs in fp32 in the reference
+        A.coef[b] = image_coef(A.cost, b, A.C, A.q, A.lamda, Bg, &S);
         const float Wb = A.q == 2.0f ? sqrtf(S) : powf(S, 1.0f / A.q);
         acc += (double)Wb;
-        A.coef[b] = S > 0.f ? (double)A.lamda / Bg * (1.0 / A.q) * pow((double)S, 1.0 / (double)A.q - 1.0)
-                            : __longlong_as_double(0x7FF8000000000000LL);
         if (A.loss_r) for (int c = 0; c < A.C; ++c) reg += A.tpers[b * A.C + c];
     }
     acc = block_sum(acc, s_red);
@@ -205,61 +204,6 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs A) {
         if (A.loss_r) loss += reg / ((double)Bg * A.C);
         // an exhausted arena / basin table or a NaN pixel makes the pairing incomplete: fail loudly
         *A.loss_out = (A.status && *A.status) ? __int_as_float(0x7FC00000) : (float)((double)A.lamda * loss);
-    }
-}
-
-struct GradArgs {
-    const PairRec* arena; const uint32_t* offs; const int32_t* counts; const double* coef; const float* grad_loss;
-    int M, C, N, B_global, loss_r;
-    float q, lamda;
-    float* grad_pred;
-};
-
-// One CTA per map: zero-fill the map's gradient (128-bit stores, the lines stay in L2), then scatter-add
-// the pairs into the critical pixels.  Fusing the fill keeps the atomics off cold DRAM lines and saves the
-// separate memset pass.
-__global__ void __launch_bounds__(512) grad_kernel(GradArgs A) {
-    const double gl = A.grad_loss ? (double)__ldg(A.grad_loss) : 1.0;
-    const double q = (double)A.q;
-    for (int map = blockIdx.x; map < A.M; map += gridDim.x) {
-        const int n = A.counts[map];
-        const PairRec* recs = A.arena + A.offs[map];
-        float* g = A.grad_pred + (size_t)map * A.N;
-        if (((reinterpret_cast<uintptr_t>(g) & 15) == 0) && (A.N & 3) == 0) {
-            float4* g4 = reinterpret_cast<float4*>(g);
-            for (int i = threadIdx.x; i < (A.N >> 2); i += blockDim.x) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            for (int i = threadIdx.x; i < A.N; i += blockDim.x) g[i] = 0.f;
-        }
-        __syncthreads();  // the fill is visible to the whole CTA before its atomics land on the same lines
-        const double coef = A.coef[map / A.C] * gl;
-        const double creg = (double)A.lamda / ((double)A.B_global * A.C) * gl;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const PairRec r = recs[i];
-            double gb, gd;
-            if (isnan(r.tb)) {  // matched to the diagonal
-                const float h = 0.5f * (r.b + r.d);
-                const float x = fmaxf(fabsf(r.b - h), fabsf(r.d - h));
-                const double gg = x > 0.f ? (q == 2.0 ? 2.0 * (double)x : q * pow((double)x, q - 1.0)) : (q == 1.0 ? 1.0 : 0.0);
-                const double s = r.d > r.b ? 1.0 : (r.d < r.b ? -1.0 : 0.0);
-                gb = -0.5 * gg * s; gd = 0.5 * gg * s;
-            } else {
-                const float xb = r.b - r.tb, xd = r.d - r.td, ab = fabsf(xb), ad = fabsf(xd);
-                const float dist = fmaxf(ab, ad);
-                const double gg = dist > 0.f ? q * pow((double)dist, q - 1.0) : 0.0;
-                gb = ab == dist ? gg * (xb > 0.f ? 1.0 : (xb < 0.f ? -1.0 : 0.0)) : 0.0;
-                gd = ad == dist ? gg * (xd > 0.f ? 1.0 : (xd < 0.f ? -1.0 : 0.0)) : 0.0;
-            }
-            gb *= coef; gd *= coef;  // NaN coefficient (S_b == 0) poisons every entry, like autograd
-            if (A.loss_r) {
-                const double pers = (double)r.d - (double)r.b, ap = fabs(pers);
-                const double gr = ap > 0.0 ? q * pow(ap, q - 1.0) * (pers > 0.0 ? 1.0 : -1.0) * creg : 0.0;
-                gb -= gr; gd += gr;
-            }
-            atomicAdd(g + r.cre, (float)gb);
-            atomicAdd(g + r.des, (float)gd);
-        }
-        __syncthreads();
     }
 }
 

@@ -38,7 +38,8 @@ struct MatchFwdArgs {
 constexpr int kColCache = 12288;  // columns (b, d) kept in dynamic shared memory: 96 KB
 
 // one map; every thread of a kMatchThreads-wide CTA calls this (block-uniform); s_col: kColCache points of scratch
-__device__ __noinline__ void match_one_map(const MatchFwdArgs& A, int k, float2* s_col) {
+// returns (block-uniform) whether the map went to the heavy list instead of being matched here
+__device__ __noinline__ bool match_one_map(const MatchFwdArgs& A, int k, float2* s_col) {
     __shared__ double s_red[kMatchThreads / 32];
     __shared__ double s_bv[kMatchThreads / 32];
     __shared__ int s_bk[kMatchThreads / 32], s_bw[kMatchThreads / 32];
@@ -66,7 +67,7 @@ __device__ __noinline__ void match_one_map(const MatchFwdArgs& A, int k, float2*
             if (R == 0) A.cost[k] = A.ps.dsum[0][k] + A.ps.dsum[1][k];
             else A.heavy[atomicAdd(A.n_heavy, 1u)] = k;
         }
-        return;
+        return R != 0;
     }
     const PairRec* rR = swp ? rec1 : rec2;
     const PairRec* rC = swp ? rec2 : rec1;
@@ -167,6 +168,7 @@ __device__ __noinline__ void match_one_map(const MatchFwdArgs& A, int k, float2*
         A.cost[k] = total;
         A.tpers[k] = tp;
     }
+    return false;
 }
 
 __global__ void __launch_bounds__(kMatchThreads) match_small_kernel(const __grid_constant__ MatchFwdArgs A) {

@@ -18,6 +18,7 @@
 #include "ph_kernel.cuh"
 #include "ph_binary.cuh"
 #include "match_small.cuh"
+#include "grad_kernel.cuh"
 
 namespace tl {
 
@@ -437,6 +438,13 @@ __device__ __noinline__ void band_merge(const BandMergeArgs& B TL_SPARAM) {
     __syncthreads();
 }
 
+// the gradient job of the launch's tail, out of line so that its registers are not the main path's
+constexpr int kGradTilePx = 32768;  // 128 KB of the tail's shared memory
+__device__ __noinline__ void grad_job(const GradArgs& A, int map, double coef, float* tile, unsigned long long* dbg) {
+    if (A.N <= 4 * kGradTilePx) grad_one_map_tiled(A, map, coef, 1.0, tile, kGradTilePx, dbg);  // block-uniform
+    else grad_one_map(A, map, coef, 1.0);
+}
+
 struct PhSmallArgs {
     PhArgs base;
     CrossEdge* elist;    // [grid][e_stride] edges that cross two basins
@@ -447,12 +455,26 @@ struct PhSmallArgs {
     size_t k_stride;
     unsigned long long* prof;  // optional [8] phase cycle counters
     int binary_path;           // 1: try the two-valued fast path first (H1)
-    // tl_forward only: CTAs that have run out of persistence jobs match the maps whose two diagrams are complete
-    // (ready[k] == 2), so the matching runs in the tail of this launch instead of a launch of its own
+    // tl_forward only: the SM that completes a map's second diagram writes the map's cost itself when one of the two
+    // diagrams is empty (ready[k] = 4), else hands the map (ready[k] = 3) to the CTAs that have run out of persistence
+    // jobs: the matching runs in the tail of this launch instead of a launch of its own
     int fuse_match;
     unsigned int* ready;       // [n_maps] sets of map k that are finished (device counters, zeroed by the host)
     MatchFwdArgs mf;
+    // tl_forward_backward only: the same tail also writes the gradient (upstream 1.0) of every image whose C maps are
+    // matched.  An image is PUBLISHED by the CTA that matches its last map: gq[slot] = kGqValid | image (| kGqSkip when
+    // one of its maps went to the heavy list: tl_backward's grad_kernel serves those); its C maps are C gradient jobs,
+    // claimed in publication order from gq_head -- only jobs whose image is already published, so nobody waits while holding one.
+    int fuse_grad;
+    GradArgs ga;               // coef / grad_loss unused: the coefficient is formed from `cost` per job
+    const double* cost;        // [n_maps] matching cost per map (MatchFwdArgs::cost)
+    unsigned int* img_cnt;     // [B] low 16 bits: matched maps of the image, high 16: of those, maps on the heavy list
+    unsigned int* gq;          // [B] publication queue
+    unsigned int* gq_tail;     // images published
+    unsigned int* gq_head;     // gradient jobs claimed
+    uint32_t* gfused;          // [B] 1: the image's gradient has been written here
 };
+constexpr unsigned int kGqValid = 0x80000000u, kGqSkip = 0x40000000u, kGqImage = 0x00FFFFFFu;
 
 template <int DIM>
 struct SmallCtx {
@@ -535,10 +557,44 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
 
     if (tid == 0) s_next = atomicAdd(A.job_counter, 1u);
     int finished_map = -1;  // (thread 0) map of the job just completed, to be published
+    // (thread 0, tl_forward_backward) map k has its final cost -- or sits on the heavy list: count it for its image and,
+    // when it is the image's last map, publish the image to the gradient queue
+    auto map_matched = [&](int k, bool heavy) {
+        __threadfence();
+        const unsigned int b = (unsigned int)(k / S.ga.C);
+        const unsigned int old = atomicAdd(S.img_cnt + b, heavy ? 0x10001u : 1u);
+        if ((old & 0xFFFFu) + 1u == (unsigned int)S.ga.C) {
+            const bool skip = (old >> 16) != 0u || heavy;
+            if (!skip) S.gfused[b] = 1u;
+            const unsigned int slot = atomicAdd(S.gq_tail, 1u);
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(S.gq + slot), "r"(kGqValid | (skip ? kGqSkip : 0u) | b) : "memory");
+        }
+    };
     for (;;) {
         __syncthreads();
-        // publish the finished job: every thread's records are written (barrier above), release them device-wide
-        if (tid == 0 && finished_map >= 0 && S.fuse_match) { __threadfence(); atomicAdd(S.ready + finished_map, 1u); }
+        // publish the finished job: every thread's records are written (barrier above), release them device-wide.
+        // ready[k]: 0 / 1 / 2 = finished diagrams of map k; the SM that finishes the second one then sets 3 = "both
+        // complete, to be matched by a job of the tail" or -- when one of the diagrams is empty, most maps with
+        // segmentation ground truth: the cost is the two diagonal sums -- writes the cost itself and sets 4 = "matched"
+        if (tid == 0 && finished_map >= 0 && S.fuse_match) {
+            __threadfence();
+            if (atomicAdd(S.ready + finished_map, 1u) == 1u) {
+                unsigned int st = 3u;
+                if (!S.mf.loss_r) {
+                    __threadfence();
+                    const int n0 = __ldcg(A.ps.counts[0] + finished_map), n1 = __ldcg(A.ps.counts[1] + finished_map);
+                    if (n0 == 0 || n1 == 0) {
+                        S.mf.cost[finished_map] = __ldcg(A.ps.dsum[0] + finished_map) + __ldcg(A.ps.dsum[1] + finished_map);
+                        S.mf.tpers[finished_map] = 0.0;
+                        st = 4u;
+                        if (S.fuse_grad) map_matched(finished_map, false);
+                    }
+                }
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(S.ready + finished_map), "r"(st) : "memory");
+            }
+        }
         // one job is always claimed ahead: its map is prefetched into L2 while this one is being emitted
         if (tid == 0) { s_job = s_next; s_next = atomicAdd(A.job_counter, 1u); s_count = 0; s_ncross = 0; s_nx = 0; s_nan = 0; s_argmax = 0ull; s_lo = 0xFFFFFFFFu; s_hi = 0u; }
         __syncthreads();
@@ -1454,25 +1510,90 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
         TL_PROF(5);
     }
     // ---- tail of the launch: this SM has no persistence job left.  Match the maps whose prediction and ground-truth
-    //      diagrams are both complete (the other SMs are still finishing theirs), one map per claim.
+    //      diagrams are both complete (the other SMs are still finishing theirs) and, for tl_forward_backward, write
+    //      the gradient of the images whose maps are all matched.  Thread 0 is the scheduler.  Jobs of both kinds are
+    //      claimed with a fetch-add (a compare-and-swap claim serialises the 148 SMs on one word: measured 0.4 ms), so
+    //      a claimed job may not be runnable yet (matching: ready[k] < 3; gradient: image not published): the SM keeps
+    //      at most one job of each kind in hand and runs whichever becomes runnable first.  No cycle of waits: a held
+    //      gradient job waits for matching jobs, which wait for persistence jobs, which wait for nothing, and an SM
+    //      holding a gradient job keeps claiming and running matching jobs.  The next job of a kind is claimed right
+    //      before the current one runs, so the claim's round trip to L2 hides behind the job.
+    // TL_OPT_PROFILE: per-CTA timeline of the tail (ns, %globaltimer) in the CTA's own root-pixel scratch, free by now:
+    // [0] persistence jobs done  [1] exit  [2] ns in matching jobs  [3] ns in gradient jobs  [4] matching jobs  [5] gradient jobs
+    unsigned long long tp_t0 = 0ull, tp_match = 0ull, tp_grad = 0ull, tp_nm = 0ull, tp_ng = 0ull;
+    auto now_ns = [] { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
+    if (S.prof && tid == 0) tp_t0 = now_ns();
+    __shared__ unsigned long long s_gdbg[5];
+    if (tid == 0) s_gdbg[0] = s_gdbg[1] = s_gdbg[2] = s_gdbg[3] = s_gdbg[4] = 0ull;
     if (S.fuse_match) {
+        __shared__ int s_kind, s_arg;
+        __shared__ double s_coef;
+        const int n_maps = S.mf.n_maps, Cc = S.ga.C;
+        const unsigned int n_gjobs = S.fuse_grad ? (unsigned int)n_maps : 0u;
+        // (thread 0) claimed job of each kind: kNoJob = none in hand, >= limit = that kind is exhausted
+        constexpr unsigned int kNoJob = 0xFFFFFFFFu;
+        unsigned int held_m = kNoJob, held_g = kNoJob;
+        bool m_done = false, g_done = n_gjobs == 0u;
+        if (tid == 0) {
+            held_m = atomicAdd(S.mf.counter, 1u);
+            if (!g_done) held_g = atomicAdd(S.gq_head, 1u);
+        }
         for (;;) {
             __syncthreads();
-            if (tid == 0) s_job = atomicAdd(S.mf.counter, 1u);
-            __syncthreads();
-            const int k = (int)s_job;
-            if (k >= S.mf.n_maps) break;
             if (tid == 0) {
-                unsigned int v;
+                int kind = 0, arg = 0;
                 for (;;) {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(S.ready + k) : "memory");
-                    if (v >= 2u) break;
-                    __nanosleep(200);
+                    if (!m_done && held_m == kNoJob) held_m = atomicAdd(S.mf.counter, 1u);
+                    if (!g_done && held_g == kNoJob) held_g = atomicAdd(S.gq_head, 1u);
+                    if (!m_done && held_m >= (unsigned int)n_maps) { m_done = true; held_m = kNoJob; }
+                    if (!g_done && held_g >= n_gjobs) { g_done = true; held_g = kNoJob; }
+                    if (held_m != kNoJob) {
+                        unsigned int v;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(S.ready + held_m) : "memory");
+                        if (v >= 4u) { held_m = kNoJob; continue; }  // matched where its second diagram was finished
+                        if (v == 3u) { kind = 1; arg = (int)held_m; held_m = kNoJob; break; }
+                    }
+                    if (held_g != kNoJob) {
+                        unsigned int e;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(S.gq + held_g / (unsigned int)Cc) : "memory");
+                        if (e & kGqValid) {
+                            const unsigned int ch = held_g % (unsigned int)Cc;
+                            held_g = kNoJob;
+                            if (e & kGqSkip) continue;  // left to grad_kernel
+                            kind = 2; arg = (int)((e & kGqImage) * (unsigned int)Cc + ch);
+                            break;
+                        }
+                    }
+                    if (m_done && g_done) break;  // nothing in hand, nothing left to claim
+                    __nanosleep(100);
                 }
+                s_kind = kind; s_arg = arg;
+                if (kind == 2) s_coef = image_coef(S.cost, arg / Cc, Cc, S.ga.q, S.ga.lamda, S.ga.B_global, nullptr);
+                // claim ahead: the value is not looked at before the next scheduling round
+                if (kind == 1 && !m_done) held_m = atomicAdd(S.mf.counter, 1u);
+                if (kind == 2 && !g_done) held_g = atomicAdd(S.gq_head, 1u);
             }
             __syncthreads();
-            match_one_map(S.mf, k, reinterpret_cast<float2*>(smem));
+            const int kind = s_kind, k = s_arg;
+            if (kind == 0) break;
+            unsigned long long tj = 0ull;
+            if (S.prof && tid == 0) tj = now_ns();
+            if (kind == 1) {
+                const bool heavy = match_one_map(S.mf, k, reinterpret_cast<float2*>(smem));
+                if (S.fuse_grad && tid == 0) map_matched(k, heavy);  // thread 0 wrote the map's cost and matched points itself
+            } else {
+                grad_job(S.ga, k, s_coef, reinterpret_cast<float*>(smem), S.prof ? s_gdbg : nullptr);
+            }
+            if (S.prof && tid == 0) {
+                const unsigned long long dt = now_ns() - tj;
+                if (kind == 1) { tp_match += dt; ++tp_nm; } else { tp_grad += dt; ++tp_ng; }
+            }
         }
+    }
+    if (S.prof && tid == 0) {
+        unsigned long long* o = reinterpret_cast<unsigned long long*>(S.rootpix + (size_t)blockIdx.x * S.k_stride);
+        o[0] = tp_t0; o[1] = now_ns(); o[2] = tp_match; o[3] = tp_grad; o[4] = tp_nm; o[5] = tp_ng;
+        if (S.fuse_match) { o[6] = s_gdbg[0]; o[7] = s_gdbg[1]; o[8] = s_gdbg[2]; o[9] = s_gdbg[3]; o[10] = s_gdbg[4]; } else o[6] = o[7] = o[8] = o[9] = o[10] = 0ull;
     }
 #undef TL_PROF
 }

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "dice_ce_kernel.cuh"
+#include "mask_kernel.cuh"
 #include "match_kernel.cuh"
 #include "ph_kernel.cuh"
 #include "ph_small.cuh"
@@ -46,6 +47,7 @@ struct Options {
         v[TL_OPT_NO_BINARY_PATH] = env1("TL_NO_BINARY");
         v[TL_OPT_WORST_CASE_WORKSPACE] = env1("TL_WORST_CASE_WORKSPACE");
         v[TL_OPT_NO_FUSED_MATCH] = env1("TL_NO_FUSED_MATCH");
+        v[TL_OPT_NO_FUSED_GRAD] = env1("TL_NO_FUSED_GRAD");
     }
 };
 Options g_opt;
@@ -108,10 +110,11 @@ int sm_count() {  // per call: the device may differ between calls (one process,
 
 // STATE (kept from tl_forward to tl_backward): header, per-map bookkeeping, the pair arena.
 //   header: [0] job counter (u32) | [8] arena head (u64) | [16] status (u32) | [20] heavy count (u32) |
-//           [24] match work counter (u32) | [64..127] phase cycle counters (8 x u64)
+//           [24] match work counter (u32) | [28] images published (u32) | [32] gradient jobs claimed (u32) |
+//           [64..127] phase cycle counters (8 x u64)
 struct StateLayout {
     int M;
-    size_t counts[2], offs[2], dsum[2], cost, tpers, coef, heavy, ready, arena, fixed;
+    size_t counts[2], offs[2], dsum[2], cost, tpers, coef, heavy, ready, img_cnt, gq, gfused, sync_end, arena, fixed;
     unsigned long long arena_default;  // records tl_workspace_bytes asks for
 };
 StateLayout make_state(int M, int H, int W, int dim, int B) {
@@ -127,7 +130,12 @@ StateLayout make_state(int M, int H, int W, int dim, int B) {
     L.tpers = take(sizeof(double) * (size_t)M);
     L.coef = take(sizeof(double) * (size_t)(B > 0 ? B : 1));
     L.heavy = take(sizeof(int32_t) * (size_t)M);
+    // ready .. gfused: the launch's synchronisation words, zeroed by ONE memset per call
     L.ready = take(sizeof(uint32_t) * (size_t)M);
+    L.img_cnt = take(sizeof(uint32_t) * (size_t)(B > 0 ? B : 1));
+    L.gq = take(sizeof(uint32_t) * (size_t)(B > 0 ? B : 1));
+    L.gfused = take(sizeof(uint32_t) * (size_t)(B > 0 ? B : 1));
+    L.sync_end = o;
     L.arena = o;
     L.fixed = o;
     // Records for both sets together.  Worst case: max_pairs per map and set.  Typical: noise-like
@@ -242,7 +250,7 @@ tl::PairStore pair_store(void* state, const StateLayout& L, size_t state_bytes, 
 // *fused tells the caller whether it did (the global-memory kernel does not)
 int launch_ph(const float* m0, const float* m1, int n_sets, int M, const tl::PairStore& ps, const ScratchLayout& L, int H, int W,
               int dim, void* state, void* scratch, cudaStream_t st, const tl::MatchFwdArgs* mf = nullptr, unsigned int* ready = nullptr,
-              bool* fused = nullptr) {
+              bool* fused = nullptr, const tl::GradArgs* ga = nullptr, const StateLayout* SL = nullptr) {
     if (fused) *fused = false;
     tl::PhArgs a;
     a.maps[0] = m0; a.maps[1] = m1;
@@ -269,11 +277,27 @@ int launch_ph(const float* m0, const float* m1, int n_sets, int M, const tl::Pai
         sa.binary_path = !opt(TL_OPT_NO_BINARY_PATH);
         sa.fuse_match = mf != nullptr && !opt(TL_OPT_NO_FUSED_MATCH);
         sa.ready = ready;
+        sa.fuse_grad = 0;
+        memset(&sa.ga, 0, sizeof(sa.ga));
+        sa.cost = nullptr; sa.img_cnt = sa.gq = sa.gq_tail = sa.gq_head = nullptr; sa.gfused = nullptr;
         if (sa.fuse_match) {
             sa.mf = *mf;
-            TL_CUDA(cudaMemsetAsync(ready, 0, sizeof(uint32_t) * (size_t)M, st));
+            if (SL) TL_CUDA(cudaMemsetAsync(at<char>(state, SL->ready), 0, SL->sync_end - SL->ready, st));
+            else TL_CUDA(cudaMemsetAsync(ready, 0, sizeof(uint32_t) * (size_t)M, st));
             if (fused) *fused = true;
-        } else memset(&sa.mf, 0, sizeof(sa.mf));
+            // the gradient rides in the same tail (tl_forward_backward); the per-image counter has 16 bits per field
+            if (ga && SL && ga->C <= 0xFFFF && M / ga->C <= 0xFFFFFF && !opt(TL_OPT_NO_FUSED_GRAD)) {
+                sa.fuse_grad = 1;
+                sa.ga = *ga;
+                sa.cost = mf->cost;
+                sa.img_cnt = at<unsigned int>(state, SL->img_cnt); sa.gq = at<unsigned int>(state, SL->gq);
+                sa.gq_tail = at<unsigned int>(state, 28); sa.gq_head = at<unsigned int>(state, 32);
+                sa.gfused = at<uint32_t>(state, SL->gfused);
+            }
+        } else {
+            memset(&sa.mf, 0, sizeof(sa.mf));
+            if (SL) TL_CUDA(cudaMemsetAsync(at<char>(state, SL->gfused), 0, SL->sync_end - SL->gfused, st));
+        }
         // single band: at most 65536 pixels (H1; the last pixel doubles as OUTSIDE) / 65535 vertices (H0)
         const bool single = dim == 1 ? (long long)H * W <= 65536 : (long long)(H + 1) * (W + 1) <= 65535;
         auto launch = [&](auto kernel) -> int {
@@ -286,6 +310,7 @@ int launch_ph(const float* m0, const float* m1, int n_sets, int M, const tl::Pai
         else rc = single ? launch(tl::ph_small_kernel<0, false>) : launch(tl::ph_small_kernel<0, true>);
         if (rc != TL_OK) return rc;
     } else {
+        if (SL) TL_CUDA(cudaMemsetAsync(at<char>(state, SL->gfused), 0, SL->sync_end - SL->gfused, st));
         const int grid = (int)(jobs < kPhSlots ? jobs : kPhSlots);
         if (dim == 1) tl::ph_kernel<1><<<grid, tl::kPhThreads, 0, st>>>(a);
         else tl::ph_kernel<0><<<grid, tl::kPhThreads, 0, st>>>(a);
@@ -327,6 +352,17 @@ int tl_debug_profile(const void* state, unsigned long long* host_out8) {
     TL_CUDA(cudaDeviceSynchronize());
     TL_CUDA(cudaMemcpy(host_out8, static_cast<const char*>(state) + 64, 64, cudaMemcpyDeviceToHost));
     return TL_OK;
+}
+
+int tl_debug_tail_profile(const void* scratch, int H, int W, int feat_d, unsigned long long* host_out, int max_slots) {
+    if (!scratch || !host_out || max_slots <= 0) return fail(TL_ERR_ARG, "null pointer");
+    const ScratchLayout L = make_scratch(H, W, feat_d, false, 0);
+    if (!L.small) return fail(TL_ERR_ARG, "shape not served by the shared-memory kernel");
+    TL_CUDA(cudaDeviceSynchronize());
+    const int n = L.slots < max_slots ? L.slots : max_slots;
+    for (int i = 0; i < n; ++i)
+        TL_CUDA(cudaMemcpy(host_out + 11 * i, static_cast<const char*>(scratch) + L.rootpix + sizeof(uint32_t) * L.k_stride * i, 88, cudaMemcpyDeviceToHost));
+    return n;
 }
 
 int tl_status(const void* state, int* host_status, void* stream) {
@@ -390,9 +426,12 @@ int tl_workspace_bytes(int B, int C, int H, int W, int feat_d, size_t* state_byt
     return TL_OK;
 }
 
-int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W, int feat_d, float q,
-               float lamda, int loss_r, int B_global, void* state, size_t state_bytes, void* scratch,
-               size_t scratch_bytes, float* loss_out, void* stream) {
+// tl_forward (grad_pred == null) and tl_forward_backward: grad_pred, when given, receives d loss / d pred for an
+// upstream gradient of 1 -- written in the tail of the persistence launch for every image the small-R matching
+// served, by grad_kernel afterwards for the rest
+static int forward_impl(const float* pred, const float* truth, int B, int C, int H, int W, int feat_d, float q,
+                        float lamda, int loss_r, int B_global, void* state, size_t state_bytes, void* scratch,
+                        size_t scratch_bytes, float* loss_out, float* grad_pred, void* stream) {
     int rc = check_shape(B, C, H, W, feat_d);
     if (rc != TL_OK) return rc;
     if (!pred || !truth || !state || !scratch || !loss_out) return fail(TL_ERR_ARG, "null pointer");
@@ -406,6 +445,14 @@ int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const tl::PairStore ps = pair_store(state, S, state_bytes, nullptr, q);
 
+    tl::GradArgs g;
+    g.arena = at<tl::PairRec>(state, S.arena); g.offs = at<uint32_t>(state, S.offs[0]); g.counts = at<int32_t>(state, S.counts[0]);
+    g.coef = at<double>(state, S.coef); g.grad_loss = nullptr;
+    g.M = M; g.C = C; g.N = H * W; g.B_global = B_global; g.loss_r = loss_r;
+    g.q = q; g.lamda = lamda; g.grad_pred = grad_pred; g.gfused = at<uint32_t>(state, S.gfused);
+
+    bool fused = false;
+    {
     const TimingScope tm(true);
     tm.mark(0, st);
     // pairs leave the persistence kernel in a deterministic (raster) order, so the matching needs no
@@ -415,8 +462,8 @@ int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W
     mf.cost = at<double>(state, S.cost); mf.tpers = at<double>(state, S.tpers);
     mf.heavy = at<int32_t>(state, S.heavy); mf.n_heavy = at<unsigned int>(state, 20);
     mf.counter = at<unsigned int>(state, 24);
-    bool fused = false;
-    rc = launch_ph(pred, truth, 2, M, ps, L, H, W, feat_d, state, scratch, st, &mf, at<unsigned int>(state, S.ready), &fused);
+    rc = launch_ph(pred, truth, 2, M, ps, L, H, W, feat_d, state, scratch, st, &mf, at<unsigned int>(state, S.ready), &fused,
+                   grad_pred ? &g : nullptr, &S);
     if (rc != TL_OK) return rc;
     tm.mark(1, st);
     tm.mark(2, st);
@@ -447,6 +494,58 @@ int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W
     tl::loss_kernel<<<1, 256, 0, st>>>(la);
     TL_CUDA(cudaGetLastError());
     tm.mark(4, st);
+    }
+    if (grad_pred) {  // whatever the tail did not serve (all of it when the fusion is off)
+        const TimingScope tm(false);
+        tm.mark(5, st);
+        tm.mark(6, st);
+        // (with the gradient fused into the persistence launch this only serves images with maps on the heavy list:
+        // a small grid, its CTAs mostly look at gfused[] and leave)
+        const bool in_tail = fused && C <= 0xFFFF && B <= 0xFFFFFF && !opt(TL_OPT_NO_FUSED_GRAD);
+        const int cap = in_tail ? 296 : 1184;
+        tl::grad_kernel<<<M < cap ? M : cap, 512, 0, st>>>(g);
+        TL_CUDA(cudaGetLastError());
+        tm.mark(7, st);
+    }
+    return TL_OK;
+}
+
+int tl_forward(const float* pred, const float* truth, int B, int C, int H, int W, int feat_d, float q,
+               float lamda, int loss_r, int B_global, void* state, size_t state_bytes, void* scratch,
+               size_t scratch_bytes, float* loss_out, void* stream) {
+    return forward_impl(pred, truth, B, C, H, W, feat_d, q, lamda, loss_r, B_global, state, state_bytes, scratch,
+                        scratch_bytes, loss_out, nullptr, stream);
+}
+
+int tl_forward_backward(const float* pred, const float* truth, int B, int C, int H, int W, int feat_d, float q,
+                        float lamda, int loss_r, int B_global, void* state, size_t state_bytes, void* scratch,
+                        size_t scratch_bytes, float* loss_out, float* grad_pred, void* stream) {
+    if (!grad_pred) return fail(TL_ERR_ARG, "null pointer");
+    return forward_impl(pred, truth, B, C, H, W, feat_d, q, lamda, loss_r, B_global, state, state_bytes, scratch,
+                        scratch_bytes, loss_out, grad_pred, stream);
+}
+
+int tl_unpack_mask_bits(const uint8_t* bits, float* maps, long long n_pixels, void* stream) {
+    if (!bits || !maps || n_pixels < 0 || (n_pixels & 7)) return fail(TL_ERR_ARG, "n_pixels must be a non-negative multiple of 8");
+    if (n_pixels == 0) return TL_OK;
+    const long long n_bytes = n_pixels >> 3;
+    long long blocks = (n_bytes / 4 + 255) / 256;
+    if (blocks > 2368) blocks = 2368;
+    if (blocks < 1) blocks = 1;
+    tl::unpack_bits_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(bits, maps, n_bytes);
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+int tl_scale_gradient(const float* grad_loss, float* grad_pred, long long n, void* stream) {
+    if (!grad_pred || n < 0) return fail(TL_ERR_ARG, "bad argument");
+    if (!grad_loss || n == 0) return TL_OK;  // NULL: upstream gradient 1.0
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    if (blocks < 1) blocks = 1;
+    tl::scale_kernel<<<(int)blocks, 256, 0, st>>>(grad_loss, grad_pred, n);
+    TL_CUDA(cudaGetLastError());
     return TL_OK;
 }
 
@@ -468,7 +567,7 @@ int tl_backward(const float* grad_loss, const void* state, size_t state_bytes, i
     g.arena = at<tl::PairRec>(w, S.arena); g.offs = at<uint32_t>(w, S.offs[0]); g.counts = at<int32_t>(w, S.counts[0]);
     g.coef = at<double>(w, S.coef); g.grad_loss = grad_loss;
     g.M = M; g.C = C; g.N = H * W; g.B_global = B_global; g.loss_r = loss_r;
-    g.q = q; g.lamda = lamda; g.grad_pred = grad_pred;
+    g.q = q; g.lamda = lamda; g.grad_pred = grad_pred; g.gfused = nullptr;  // always the full gradient
     tl::grad_kernel<<<M < 1184 ? M : 1184, 512, 0, st>>>(g);
     TL_CUDA(cudaGetLastError());
     tm.mark(7, st);

@@ -110,7 +110,12 @@ def check_status(sync: bool = True) -> None:
 class _TopoLossFn(torch.autograd.Function):
     """forward = tl_forward, backward = tl_backward (analytic backward of the reference's autograd
     graph: MulBackward / MeanBackward / PowBackward / POT ValFunction / CdistBackward /
-    IndexBackward, i.e. what ``train_loss.backward()`` at training_utils.py:66 runs for this loss)."""
+    IndexBackward, i.e. what ``train_loss.backward()`` at training_utils.py:66 runs for this loss).
+
+    When the prediction requires a gradient the forward is ``tl_forward_backward``: the gradient for an
+    upstream gradient of 1 is written in the tail of the persistence launch (by SMs that have run out of
+    persistence work), and ``backward`` only scales it -- a kernel that returns at once when the upstream
+    gradient is exactly 1, the case of ``(seg_loss + topo_loss).backward()``."""
 
     @staticmethod
     def forward(ctx, pred, truth, lamda, feat_d, loss_q, loss_r, global_batch):
@@ -118,16 +123,22 @@ class _TopoLossFn(torch.autograd.Function):
         dev = pred.device
         ring = _status_ring(dev)
         ring.poll()
+        want_grad = bool(ctx.needs_input_grad[0])
         with torch.cuda.device(dev):
             state, scratch = _buffers(B, C, H, W, feat_d, dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
-            rc = _lib.lib().tl_forward(pred.data_ptr(), truth.data_ptr(), B, C, H, W, feat_d, float(loss_q),
-                                       float(lamda), int(bool(loss_r)), int(global_batch), state.data_ptr(),
-                                       state.numel(), scratch.data_ptr(), scratch.numel(), loss.data_ptr(),
-                                       _stream_ptr(dev))
+            args = (pred.data_ptr(), truth.data_ptr(), B, C, H, W, feat_d, float(loss_q), float(lamda),
+                    int(bool(loss_r)), int(global_batch), state.data_ptr(), state.numel(), scratch.data_ptr(),
+                    scratch.numel(), loss.data_ptr())
+            ctx.grad = None
+            if want_grad:
+                ctx.grad = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+                rc = _lib.lib().tl_forward_backward(*args, ctx.grad.data_ptr(), _stream_ptr(dev))
+            else:
+                rc = _lib.lib().tl_forward(*args, _stream_ptr(dev))
             _lib.check(rc, "tl_forward")
             ring.post(state, dev)
-        ctx.ws = state  # header + bookkeeping + pair arena; the per-CTA scratch is not kept
+        ctx.ws = state  # header + bookkeeping + pair arena (a second backward over a retained graph reads it)
         ctx.args = (B, C, H, W, feat_d, float(loss_q), float(lamda), int(bool(loss_r)), int(global_batch))
         ctx.pred_meta = (pred.dtype, dev)
         return loss
@@ -140,10 +151,17 @@ class _TopoLossFn(torch.autograd.Function):
         _status_ring(dev).poll()
         with torch.cuda.device(dev):
             g = grad_out.to(device=dev, dtype=torch.float32).contiguous()
-            grad_pred = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
-            rc = _lib.lib().tl_backward(g.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), B, C, H, W, feat_d, q,
-                                        lamda, loss_r, gb, grad_pred.data_ptr(), _stream_ptr(dev))
-        _lib.check(rc, "tl_backward")
+            # the gradient the forward wrote is handed over (not kept: autograd's AccumulateGrad copies a buffer
+            # somebody else still holds, a 2 x 235 MB pass at the headline shape)
+            grad_pred, ctx.grad = ctx.grad, None
+            if grad_pred is not None:
+                rc = _lib.lib().tl_scale_gradient(g.data_ptr(), grad_pred.data_ptr(), grad_pred.numel(), _stream_ptr(dev))
+                _lib.check(rc, "tl_scale_gradient")
+            else:  # a second backward over a retained graph: from the pairs
+                grad_pred = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+                rc = _lib.lib().tl_backward(g.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), B, C, H, W, feat_d, q,
+                                            lamda, loss_r, gb, grad_pred.data_ptr(), _stream_ptr(dev))
+                _lib.check(rc, "tl_backward")
         return grad_pred, None, None, None, None, None, None
 
 
@@ -382,12 +400,24 @@ def topo_loss_from_logits(masks, gt_masks, lamda, interp=0, feat_d=2, loss_q=2, 
 _COPY_STREAMS = {}
 
 
+def pack_mask_bits(true_host: torch.Tensor) -> torch.Tensor:
+    """{0, 1} masks ``[B, C, H, W]`` (any dtype, host) -> pinned ``uint8 [B, C, H, W // 8]``, 8 pixels per byte in
+    ``numpy.packbits`` order: the form ``topo_loss_from_host(..., truth_packed=True)`` takes.  W must be a multiple
+    of 8."""
+    if true_host.dim() != 4 or true_host.shape[-1] % 8:
+        raise ValueError("expected [B, C, H, W] with W a multiple of 8")
+    import numpy as np
+    bits = np.packbits(true_host.cpu().numpy() != 0, axis=-1)
+    return torch.from_numpy(bits).pin_memory()
+
+
 def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=2, loss_r=False, *,
-                        device=None, chunks=4, want_grad=True):
+                        device=None, chunks=4, want_grad=True, truth_packed=False):
     """``topo_loss`` for inputs that live in pinned HOST memory: forward + backward with the
     host->device copies pipelined against the kernels.  ``true_host`` may be ``uint8``: one-hot / component
     masks are {0, 1} (the reference builds them on the CPU, training_utils.py:413, :432), so they can cross
-    PCIe as bytes and be widened on the device (5 instead of 8 bytes per pixel and step).
+    PCIe as bytes and be widened on the device (5 instead of 8 bytes per pixel and step) -- or, with
+    ``truth_packed=True``, as BITS: ``uint8 [B, C, H, W // 8]`` from ``pack_mask_bits`` (4.125 bytes per pixel).
 
     The batch is cut into at most ``chunks`` groups of whole images (one wave of the persistence kernel each when
     ``chunks`` allows it); group i+1 is copied on a side stream
@@ -401,7 +431,11 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
         return 0.0, None
     if interp != 0:
         raise ValueError("topo_loss_from_host takes maps at their final resolution (interp=0)")
-    if pred_host.shape != true_host.shape or pred_host.dim() != 4:
+    if truth_packed:
+        if (pred_host.dim() != 4 or pred_host.shape[-1] % 8 or true_host.dtype != torch.uint8
+                or tuple(true_host.shape) != tuple(pred_host.shape[:-1]) + (pred_host.shape[-1] // 8,)):
+            raise ValueError("truth_packed: expected uint8 [B, C, H, W // 8] next to a [B, C, H, W] prediction, W % 8 == 0")
+    elif pred_host.shape != true_host.shape or pred_host.dim() != 4:
         raise ValueError("expected two [B, C, H, W] tensors of the same shape")
     if pred_host.dtype != torch.float32 or true_host.dtype not in (torch.float32, torch.uint8):
         raise ValueError("topo_loss expects a float32 prediction and float32 (or uint8 {0, 1}) ground truth")
@@ -421,7 +455,7 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
     orig_shape = None
     if B == 1:  # the reference's .squeeze() quirk: every channel is its own image
         orig_shape = (B, C, H, W)
-        pred_host, true_host = pred_host.reshape(C, 1, H, W), true_host.reshape(C, 1, H, W)
+        pred_host, true_host = pred_host.reshape(C, 1, H, W), true_host.reshape(C, 1, H, -1)
         B, C = C, 1
     L = _lib.lib()
     # The persistence kernel runs one prediction map per SM at a time, so a group of `sms // C` images is one
@@ -444,7 +478,7 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
         side.wait_stream(cur)
         pred = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
         truth = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
-        truth_u8 = torch.empty((B, C, H, W), dtype=torch.uint8, device=dev) if true_host.dtype == torch.uint8 else None
+        truth_u8 = torch.empty(tuple(true_host.shape), dtype=torch.uint8, device=dev) if true_host.dtype == torch.uint8 else None
         grad = torch.empty((B, C, H, W), dtype=torch.float32, device=dev) if want_grad else None
         parts = torch.empty((chunks,), dtype=torch.float32, device=dev)
         events = []
@@ -462,16 +496,19 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
         for i in range(chunks):
             a, b = bounds[i], bounds[i + 1]
             cur.wait_event(events[i])
-            if truth_u8 is not None:  # {0, 1} masks travelled as bytes: widen them on the device
+            if truth_packed:          # {0, 1} masks travelled as bits
+                _lib.check(L.tl_unpack_mask_bits(truth_u8[a:b].data_ptr(), truth[a:b].data_ptr(), (b - a) * C * H * W,
+                                                 cur.cuda_stream), "tl_unpack_mask_bits")
+            elif truth_u8 is not None:  # ... as bytes: widen them on the device
                 truth[a:b].copy_(truth_u8[a:b])
-            rc = L.tl_forward(pred[a:b].data_ptr(), truth[a:b].data_ptr(), b - a, C, H, W, feat_d, float(loss_q),
-                              float(lamda), int(bool(loss_r)), B, state.data_ptr(), state.numel(),
-                              scratch.data_ptr(), scratch.numel(), parts[i:].data_ptr(), cur.cuda_stream)
+            args = (pred[a:b].data_ptr(), truth[a:b].data_ptr(), b - a, C, H, W, feat_d, float(loss_q),
+                    float(lamda), int(bool(loss_r)), B, state.data_ptr(), state.numel(),
+                    scratch.data_ptr(), scratch.numel(), parts[i:].data_ptr())
+            if want_grad:  # loss and gradient of the group in one launch sequence
+                rc = L.tl_forward_backward(*args, grad[a:b].data_ptr(), cur.cuda_stream)
+            else:
+                rc = L.tl_forward(*args, cur.cuda_stream)
             _lib.check(rc, "tl_forward")
-            if want_grad:
-                rc = L.tl_backward(None, state.data_ptr(), state.numel(), b - a, C, H, W, feat_d, float(loss_q),
-                                   float(lamda), int(bool(loss_r)), B, grad[a:b].data_ptr(), cur.cuda_stream)
-                _lib.check(rc, "tl_backward")
         ring.post(state, dev)  # the last group's status; the loss carries a NaN for any group
         loss = parts.sum()
         for t in (pred, truth, truth_u8, state):  # allocated on this stream, last used here or on the copy stream

@@ -46,7 +46,7 @@ extern "C" {
 #define TL_ERR_WORKSPACE (-2) /* workspace too small */
 #define TL_ERR_CUDA (-3)      /* a CUDA runtime call failed; see tl_last_error() */
 
-#define TL_ABI_VERSION 2
+#define TL_ABI_VERSION 3
 
 /* ABI version of the loaded library (TL_ABI_VERSION it was built with). */
 int tl_version(void);
@@ -56,7 +56,7 @@ const char* tl_last_error(void);
 
 /*
  * Process-wide options.  Initial values are read from the environment ONCE, when the library is
- * loaded (TL_FORCE_GLOBAL, TL_PROFILE, TL_NO_BINARY, TL_WORST_CASE_WORKSPACE, TL_NO_FUSED_MATCH = "1"); tl_set_option
+ * loaded (TL_FORCE_GLOBAL, TL_PROFILE, TL_NO_BINARY, TL_WORST_CASE_WORKSPACE, TL_NO_FUSED_MATCH, TL_NO_FUSED_GRAD = "1"); tl_set_option
  * changes them afterwards.  FORCE_GLOBAL_KERNEL and WORST_CASE_WORKSPACE change the workspace layout:
  * use the same setting for tl_workspace_bytes and the calls that consume its sizes.
  */
@@ -65,7 +65,8 @@ const char* tl_last_error(void);
 #define TL_OPT_NO_BINARY_PATH 2       /* measurement: two-valued maps through the generic path */
 #define TL_OPT_WORST_CASE_WORKSPACE 3 /* size every table for the worst case: no input can overflow */
 #define TL_OPT_NO_FUSED_MATCH 4       /* measurement: matching in a launch of its own instead of the persistence kernel's tail */
-#define TL_OPT_COUNT_ 5
+#define TL_OPT_NO_FUSED_GRAD 5        /* measurement: tl_forward_backward writes the gradient in a launch of its own */
+#define TL_OPT_COUNT_ 6
 int tl_set_option(int which, int value);
 int tl_get_option(int which);
 
@@ -123,6 +124,31 @@ int tl_backward(const float* grad_loss, const void* state, size_t state_bytes,
                 int B_global, float* grad_pred, void* stream);
 
 /*
+ * tl_forward and tl_backward (upstream gradient 1.0) as ONE call: what `loss = topo_loss(...); loss.backward()`
+ * at training_utils.py:64-66 amounts to.  Same arguments and results as the two calls; grad_pred[B,C,H,W] is fully
+ * overwritten.  The gradient of an image is written in the tail of the persistence launch as soon as its C maps
+ * are matched, by SMs that have run out of persistence work, instead of in a launch of its own.  Scale the
+ * result with tl_scale_gradient when the upstream gradient is not 1.
+ */
+int tl_forward_backward(const float* pred, const float* truth, int B, int C, int H, int W,
+                        int feat_d, float q, float lamda, int loss_r, int B_global,
+                        void* state, size_t state_bytes, void* scratch, size_t scratch_bytes,
+                        float* loss_out, float* grad_pred, void* stream);
+
+/*
+ * grad_pred[0..n) *= *grad_loss (one fp32 on the device; NULL = 1.0).  The kernel returns without touching
+ * grad_pred when the value is exactly 1.0, the case of a plain `loss.backward()`.
+ */
+int tl_scale_gradient(const float* grad_loss, float* grad_pred, long long n, void* stream);
+
+/*
+ * Ground-truth masks that crossed PCIe bit-packed: maps[i] = bit i of `bits` as 0.0f / 1.0f, numpy.packbits
+ * order (pixel 0 is bit 7 of byte 0).  n_pixels must be a multiple of 8.  The reference builds the masks on the
+ * CPU as {0.0, 1.0} arrays (training_utils.py:398, :413, :432); packed they are 1/32 of the fp32 bytes.
+ */
+int tl_unpack_mask_bits(const uint8_t* bits, float* maps, long long n_pixels, void* stream);
+
+/*
  * Inner boundary for parity tests: CubicalComplex.forward on n_maps independent HxW maps
  * (torch_topological CubicalComplex._forward -> gudhi persistence +
  * cofaces_of_persistence_pairs).  Writes, per map, up to `cap` pairs
@@ -156,6 +182,12 @@ int tl_wasserstein(const float* D1, const int32_t* off1, const float* D2, const 
  * Synchronises the device.  host_out8: 8 x uint64 on the host.
  */
 int tl_debug_profile(const void* state, unsigned long long* host_out8);
+/*
+ * Debug aid: per-SM timeline of the tail of the last persistence launch that used `scratch` while TL_OPT_PROFILE
+ * was set: 11 x uint64 per slot (ns of %globaltimer: persistence jobs done, exit; ns spent in matching / gradient
+ * jobs; matching / gradient jobs run; cycles of the gradient jobs in tile zeroing / scatter / stream-out / record wait / barrier).  Returns the number of slots written (<= max_slots).  Synchronises the device.
+ */
+int tl_debug_tail_profile(const void* scratch, int H, int W, int feat_d, unsigned long long* host_out, int max_slots);
 
 /*
  * Measurement aid for bench.py's roofline: while enabled (process-wide, mutex-guarded: the backward

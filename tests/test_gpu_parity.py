@@ -500,6 +500,14 @@ def test_host_api_uint8_truth_and_batch_of_one():
     loss, grad = tlb.topo_loss_from_host(pred.pin_memory(), truth.to(torch.uint8).pin_memory(), 0.1, feat_d=1, chunks=3)
     assert abs(float(loss) - want_loss) <= REL * abs(want_loss)
     assert np.abs(grad.cpu().numpy() - want_grad).max() <= REL * np.abs(want_grad).max()
+    # ... and as bits (numpy.packbits order), widened by tl_unpack_mask_bits
+    bits = tlb.pack_mask_bits(truth)
+    assert bits.dtype == torch.uint8 and tuple(bits.shape) == (5, 3, 64, 8) and bits.is_pinned()
+    loss_b, grad_b = tlb.topo_loss_from_host(pred.pin_memory(), bits, 0.1, feat_d=1, chunks=2, truth_packed=True)
+    assert float(loss_b) == float(loss)
+    assert float((grad_b - grad).abs().max()) <= 1e-6 * float(grad.abs().max())  # atomics may add in another order
+    with pytest.raises(ValueError, match="truth_packed"):
+        tlb.topo_loss_from_host(pred.pin_memory(), truth.to(torch.uint8).pin_memory(), 0.1, feat_d=1, truth_packed=True)
     p1, t1 = pred[:1].contiguous(), truth[:1].contiguous()
     w1, g1 = _loss_and_grad(p1, t1, 0.1, feat_d=1)
     loss1, grad1 = tlb.topo_loss_from_host(p1.pin_memory(), t1.pin_memory(), 0.1, feat_d=1)
@@ -545,3 +553,58 @@ def test_loss_many_maps_with_two_large_diagrams():
     truth = torch.nn.functional.avg_pool2d(torch.rand((8, 6, 80, 80), generator=rng), 2)
     for _ in range(2):
         _check_loss(pred, truth, 0.1, 1)
+
+
+def test_fused_gradient_equals_separate_launch():
+    """tl_forward_backward (gradient written in the tail of the persistence launch) against tl_forward + tl_backward,
+    with images that take the small-R matching, images with maps on the heavy list (left to grad_kernel) and more
+    images than SMs' worth of jobs; then the switch TL_OPT_NO_FUSED_GRAD, an upstream gradient != 1 and a second
+    backward over a retained graph."""
+    import dilabhelmholtzoct_b200 as tlb
+    from dilabhelmholtzoct_b200 import _lib
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    from dilabhelmholtzoct_b200.topological_loss import _buffers
+    L = _lib.lib()
+    pred, truth = make_batch(24, 96, 96, seed=41, n_classes=7)
+    rng = torch.Generator().manual_seed(3)
+    soft = torch.nn.functional.avg_pool2d(torch.rand((24, 7, 192, 192), generator=rng), 2)
+    truth[5], truth[17, 2] = soft[5], soft[17, 2]  # image 5: every map heavy; image 17: one heavy map
+    pred, truth = pred.cuda(), truth.cuda()
+    B, C, H, W = pred.shape
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(fused):
+        state, scratch = _buffers(B, C, H, W, 1, pred.device)
+        loss, grad = torch.zeros((), device="cuda"), torch.full_like(pred, 7.0)
+        args = (pred.data_ptr(), truth.data_ptr(), B, C, H, W, 1, 2.0, 0.1, 0, 0, state.data_ptr(), state.numel(),
+                scratch.data_ptr(), scratch.numel(), loss.data_ptr())
+        if fused:
+            assert L.tl_forward_backward(*args, grad.data_ptr(), st) == 0
+        else:
+            assert L.tl_forward(*args, st) == 0
+            assert L.tl_backward(None, state.data_ptr(), state.numel(), B, C, H, W, 1, 2.0, 0.1, 0, 0, grad.data_ptr(), st) == 0
+        torch.cuda.synchronize()
+        return float(loss), grad.cpu().numpy()
+
+    l0, g0 = run(False)
+    for _ in range(3):
+        l1, g1 = run(True)
+        assert l1 == l0
+        assert np.array_equal(g1 != 0, g0 != 0)
+        assert np.abs(g1 - g0).max() <= 1e-6 * np.abs(g0).max()  # same terms; atomics may add them in another order
+    L.tl_set_option(_lib.OPT_NO_FUSED_GRAD, 1)
+    try:
+        l2, g2 = run(True)
+    finally:
+        L.tl_set_option(_lib.OPT_NO_FUSED_GRAD, 0)
+    assert l2 == l0 and np.abs(g2 - g0).max() <= 1e-6 * np.abs(g0).max()
+    want, wgrad, _ = oracle.topo_loss(pred.cpu().numpy(), truth.cpu().numpy(), 0.1, feat_d=1)
+    assert abs(l0 - want) <= REL * abs(want) and np.abs(g0 - wgrad).max() <= REL * np.abs(wgrad).max()
+    # autograd: upstream gradient 2.5, then a second backward over the retained graph with upstream 1
+    p = pred.clone().requires_grad_(True)
+    loss = tlb.topo_loss(p, truth, 0.1, feat_d=1)
+    (loss * 2.5).backward(retain_graph=True)
+    assert np.abs(p.grad.cpu().numpy() - 2.5 * g0).max() <= 1e-6 * 2.5 * np.abs(g0).max()
+    p.grad = None
+    loss.backward()
+    assert np.abs(p.grad.cpu().numpy() - g0).max() <= 1e-6 * np.abs(g0).max()
