@@ -440,9 +440,19 @@ __device__ __noinline__ void band_merge(const BandMergeArgs& B TL_SPARAM) {
 
 // the gradient job of the launch's tail, out of line so that its registers are not the main path's
 constexpr int kGradTilePx = 32768;  // 128 KB of the tail's shared memory
-__device__ __noinline__ void grad_job(const GradArgs& A, int map, double coef, float* tile, unsigned long long* dbg) {
-    if (A.N <= 4 * kGradTilePx) grad_one_map_tiled(A, map, coef, 1.0, tile, kGradTilePx, dbg);  // block-uniform
-    else grad_one_map(A, map, coef, 1.0);
+#ifndef TL_GRAD_BULK
+#define TL_GRAD_BULK 1
+#endif
+static_assert(kGradTilePx * 4 + 2 * kGradStageBytes <= kSmallSmemBytes, "tile + two staging buffers must fit the tail's shared memory");
+// returns the updated parity bits of the two staging mbarriers (block-uniform)
+__device__ __noinline__ unsigned int grad_job(const GradArgs& A, int map, double coef, unsigned char* smem, uint32_t bars_s, unsigned int phase,
+                                              unsigned long long* dbg) {
+    float* tile = reinterpret_cast<float*>(smem);
+    if (A.N <= 4 * kGradTilePx) {  // block-uniform
+        if (TL_GRAD_BULK) return grad_one_map_tiled_bulk(A, map, coef, 1.0, tile, kGradTilePx, smem + kGradTilePx * 4, bars_s, phase, dbg);
+        grad_one_map_tiled(A, map, coef, 1.0, tile, kGradTilePx, dbg);
+    } else grad_one_map(A, map, coef, 1.0);
+    return phase;
 }
 
 struct PhSmallArgs {
@@ -1528,6 +1538,10 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
     if (S.fuse_match) {
         __shared__ int s_kind, s_arg;
         __shared__ double s_coef;
+        __shared__ __align__(8) unsigned long long s_bars[2];  // completion barriers of the gradient jobs' record stream
+        const uint32_t bars_s = (uint32_t)__cvta_generic_to_shared(s_bars);
+        unsigned int bar_phase = 0u;
+        if (tid == 0) { mbar_init(bars_s, 1u); mbar_init(bars_s + 8u, 1u); mbar_init_fence(); }
         const int n_maps = S.mf.n_maps, Cc = S.ga.C;
         const unsigned int n_gjobs = S.fuse_grad ? (unsigned int)n_maps : 0u;
         // (thread 0) claimed job of each kind: kNoJob = none in hand, >= limit = that kind is exhausted
@@ -1582,13 +1596,14 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
                 const bool heavy = match_one_map(S.mf, k, reinterpret_cast<float2*>(smem));
                 if (S.fuse_grad && tid == 0) map_matched(k, heavy);  // thread 0 wrote the map's cost and matched points itself
             } else {
-                grad_job(S.ga, k, s_coef, reinterpret_cast<float*>(smem), S.prof ? s_gdbg : nullptr);
+                bar_phase = grad_job(S.ga, k, s_coef, smem, bars_s, bar_phase, S.prof ? s_gdbg : nullptr);
             }
             if (S.prof && tid == 0) {
                 const unsigned long long dt = now_ns() - tj;
                 if (kind == 1) { tp_match += dt; ++tp_nm; } else { tp_grad += dt; ++tp_ng; }
             }
         }
+        if (tid == 0) bulk_wait_all();  // the gradient tiles this thread sent out with bulk copies are in memory
     }
     if (S.prof && tid == 0) {
         unsigned long long* o = reinterpret_cast<unsigned long long*>(S.rootpix + (size_t)blockIdx.x * S.k_stride);

@@ -235,6 +235,7 @@ tl::PairStore pair_store(void* state, const StateLayout& L, size_t state_bytes, 
     ps.skeys = skeys;
     ps.head = at<unsigned long long>(state, 8);
     ps.cap = (state_bytes - L.arena) / sizeof(tl::PairRec);
+    if (ps.cap > 1) --ps.cap;  // one spare record: the gradient's bulk copies read whole pairs of records
     if (ps.cap > 0xFFFFFFFFull) ps.cap = 0xFFFFFFFFull;  // offsets are 32-bit
     for (int s = 0; s < 2; ++s) {
         ps.offs[s] = at<uint32_t>(state, L.offs[s]);
