@@ -228,12 +228,15 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
     // at a LATER level than this edge iff e > sug -- one 64-bit compare per hop, no shifts
     uint64_t sug = 0ull, ea = 0ull, eb = 0ull;
     bool active = false, doneA = true, doneB = true;
+    // lane l's next record: elist[beg + l * S + batch]; past the lane's real records the copy writes zeros (src-size 0) from
+    // any valid address.  One pointer, advanced by a record per batch: the 64-bit index arithmetic is paid once.
+    const CrossEdge* lane_src = elist + beg + min(lane * S, max(real - 1, 0));
+    int lane_left = max(0, min(S, real - lane * S));  // real records this lane still has to fetch
 #define TL_ISSUE()                                                                              \
     do {                                                                                        \
-        const int idx_ = issued + lane, src_ = lane * S + (issued >> 5);                        \
-        const bool ok_ = src_ < real;                                                           \
-        if (idx_ < total) cp_async16_zfill(ring_s + (uint32_t)(idx_ & (kRing - 1)) * 16u, elist + beg + (ok_ ? src_ : 0), ok_ ? 16u : 0u); \
+        if (issued < total) cp_async16_zfill(ring_s + (uint32_t)((issued + lane) & (kRing - 1)) * 16u, lane_src, lane_left > 0 ? 16u : 0u); \
         cp_async_commit();                                                                      \
+        if (lane_left > 0) { --lane_left; if (lane_left > 0) ++lane_src; }                      \
         issued = min(total, issued + 32);                                                       \
     } while (0)
     if (total > 0) TL_ISSUE();
@@ -274,7 +277,7 @@ __device__ __forceinline__ void merge_warpq_packed(const Packed& T, const CrossE
                 if (!doneA) { if (ea > sug) doneA = true; else x = (uint32_t)ea & T.gmask; }
                 if (!doneB) { if (eb > sug) doneB = true; else y = (uint32_t)eb & T.gmask; }
             }
-            if (doneA && doneB) {
+            if (doneA && doneB) {  // (entering this section only once 8 or 16 lanes are ready: +3 % cycles, measured)
                 TL_STAT(2);
                 if (x == y) {
                     active = false;
@@ -949,15 +952,19 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if ((nib >> k) & 1u) {
-                                if (cid_base + rank + 1 < (int)S.k_stride) {
+                                // (a single band's tables hold the combinatorial maximum, and its root values are read
+                                // from the map when the table is set up: all lanes busy there, a fifth of them here)
+                                if (!MULTI) rootpix[rank + 1] = (uint32_t)(gx + k);
+                                else if (cid_base + rank + 1 < (int)S.k_stride) {
                                     rootpix[cid_base + rank + 1] = (uint32_t)(gx + k);
                                     zvalg[cid_base + rank + 1] = ~mono32(__ldg(f + gx + k));
                                 }
+                                // the root's entry becomes its LABEL: band-local rank + 1 (0 will stand for OUTSIDE)
+                                ++rank;
                                 if (k == 0) w.x = (w.x & 0xFFFF0000u) | (uint32_t)rank;
                                 else if (k == 1) w.x = (w.x & 0x0000FFFFu) | ((uint32_t)rank << 16);
                                 else if (k == 2) w.y = (w.y & 0xFFFF0000u) | (uint32_t)rank;
                                 else w.y = (w.y & 0x0000FFFFu) | ((uint32_t)rank << 16);
-                                ++rank;
                             }
                         }
                         *reinterpret_cast<uint2*>(par + x) = w;
@@ -966,16 +973,20 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
                 }
             }
             __syncthreads();
-            // per-node label in place: band-local basin rank, kOut16 for OUTSIDE's basin (root entries are ranks already)
+            if (tid == 0) par[kOut16] = 0;  // OUTSIDE's label (its own barrier: with the alias the entry sits in a quad the census may rewrite)
+            __syncthreads();
+            // per-node label in place: band-local basin rank + 1, 0 for OUTSIDE's basin.  Root entries are labels already;
+            // every other entry holds its root's index, or kOut16, whose entry is OUTSIDE's label: one load, no test
             for (int t = 0; t < trips; ++t) {
                 const int x = wbeg + t * 128 + lane * 4;
-                const unsigned nib = (unsigned)(rootbits >> (4 * t)) & 15u;
+                unsigned nib = (unsigned)(rootbits >> (4 * t)) & 15u;
+                if (alias && x + 3 == N - 1) nib |= 8u;  // the pixel that doubles as OUTSIDE: its entry IS OUTSIDE's label, just set
                 if (x < wend && nib != 15u) {
                     const uint2 w = *reinterpret_cast<const uint2*>(par + x);
                     uint32_t e[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (!((nib >> k) & 1u) && e[k] != kOut16) e[k] = par[e[k]];
+                        if (!((nib >> k) & 1u)) e[k] = par[e[k]];
                     *reinterpret_cast<uint2*>(par + x) = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
                 }
             }
@@ -989,8 +1000,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
             // holds its bw h-edges, then its bw + 1 v-edges): with a single band that is the global numbering.
             // Only the left edge of a band's first column leaves the band: it goes, with global labels and a
             // global edge id, to the cross-band list that grows down from the end of the CTA's list.
-            auto glab = [&](uint32_t v) { return v == kOut16 ? 0u : (uint32_t)(cid_base + 1) + v; };
-            auto llab = [&](uint32_t v) { return v == kOut16 ? 0u : v + 1u; };
+            auto glab = [&](uint32_t v) { return v ? (uint32_t)cid_base + v : 0u; };  // band-local label -> map-wide label
+            auto llab = [&](uint32_t v) { return v; };
             const int GWb = 2 * bw + 1;
             for (int t = 0; t < trips; ++t) {  // warp-uniform trip count
                 const int x = wbeg + t * 128 + lane * 4;
@@ -1351,17 +1362,22 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
         uint16_t* rp_s16 = reinterpret_cast<uint16_t*>(smem + rp_off);
         uint32_t* rp_s32 = reinterpret_cast<uint32_t*>(smem + rp_off);
         uint16_t* lst16 = reinterpret_cast<uint16_t*>(smem + ring_off);
+        // root value of basin c: the fast front end of a single-band map left it in the map (see the census)
+        const bool z_in_map = fast && !MULTI;
+        auto zval_of = [&](int c, uint32_t rp) { return z_in_map ? ~mono32(__ldg(g.f + rp)) : zvalg[c]; };
         if (packed) {
-            for (int c = tid; c <= K; c += nt) {
-                T64[c] = (~0ull << Gbits) | (uint32_t)c; Z32[c] = c ? zvalg[c] : 0u;
-                if (rp_smem) { const uint32_t rp = c ? rootpix[c] : 0u; if (rp16) rp_s16[c] = (uint16_t)rp; else rp_s32[c] = rp; }
+#pragma unroll 4
+            for (int c = tid; c <= K; c += nt) {  // (unrolled: root pixel, then its value, are dependent loads from L2)
+                const uint32_t rp = c && (rp_smem || z_in_map) ? rootpix[c] : 0u;
+                T64[c] = (~0ull << Gbits) | (uint32_t)c; Z32[c] = c ? zval_of(c, rp) : 0u;
+                if (rp_smem) { if (rp16) rp_s16[c] = (uint16_t)rp; else rp_s32[c] = rp; }
             }
         } else if (inband) {
             if (tid == 0) { TEntry e; e.ekey = kRootKey; e.target = 0u; e.zval = 0u; T.g[0] = e; }  // OUTSIDE; the bands wrote the rest
         } else {
             for (int c = tid; c <= K; c += nt) {
                 TEntry e;
-                e.ekey = kRootKey; e.target = (uint32_t)c; e.zval = c ? zvalg[c] : 0u;
+                e.ekey = kRootKey; e.target = (uint32_t)c; e.zval = c ? zval_of(c, z_in_map ? rootpix[c] : 0u) : 0u;
                 T.g[c] = e;
             }
         }
