@@ -113,6 +113,82 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "window": self.window}
 
 
+class NvmlSampler:
+    """The same reading through NVML (nvidia_ml_py) from a thread of this process, every millisecond: the
+    device-timed region is only tens of milliseconds long, which nvidia-smi's 20 ms loop samples once or twice.
+    Samples carry a host timestamp; the ones between mark() and mark_end() are reported."""
+    HW_SLOWDOWN, SW_POWER_CAP, SW_THERMAL, HW_THERMAL = 0x8, 0x4, 0x20, 0x40
+
+    def __init__(self, index: int, uuid: str = ""):
+        self.rows, self.ok, self.stop_flag = [], False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            h = None
+            if uuid:
+                for u in (uuid, uuid.encode()):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(u)
+                        break
+                    except Exception:
+                        h = None
+            self.h = h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._read()
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _read(self):
+        nv = self.nv
+        sm = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            why = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            why = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        return time.perf_counter(), sm, why
+
+    def start(self):
+        def pump():
+            while not self.stop_flag:
+                try:
+                    self.rows.append(self._read())
+                except Exception:
+                    pass
+                time.sleep(0.001)
+        self.t = threading.Thread(target=pump, daemon=True)
+        self.t.start()
+
+    def mark(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        rows, window = [r for r in self.rows if t0 <= r[0] <= t1], "timed region"
+        if not rows:
+            rows, window = [r for r in self.rows if r[0] >= t0] or self.rows, "timed + end-to-end region"
+        sm = sorted(r[1] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        names = [("hw_slowdown", self.HW_SLOWDOWN), ("hw_thermal_slowdown", self.HW_THERMAL),
+                 ("sw_thermal_slowdown", self.SW_THERMAL), ("sw_power_cap", self.SW_POWER_CAP)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": [n for n, b in names if bits & b], "samples": len(sm), "window": window,
+                "source": "NVML, 1 ms period"}
+
+
+def make_sampler(index: int, uuid: str = ""):
+    s = NvmlSampler(index, uuid)
+    return s if s.ok else ClockSampler(index)
+
+
 def cpu_arm(pred, truth, nthreads, steps, warmup):
     """Oracle port (oracle/topo_oracle.c) forward + backward on host cores; returns masks/s."""
     import oracle
@@ -256,7 +332,11 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
-    sampler = ClockSampler(local_rank)
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        uuid = ""
+    sampler = make_sampler(local_rank, uuid)
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):

@@ -167,7 +167,8 @@ ScratchLayout make_scratch(int H, int W, int dim, bool with_sort, unsigned long 
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes); return at; };
     // shared-memory kernel: processes the map in bands of whole node columns (<= 65535 nodes each)
-    L.small = (W + 1) <= tl::kSmallMaxRow && (long long)L.n_nodes < (1ll << 22);
+    // (rows are counted too: a band is at least 4 columns of ALL node rows, so n_rows <= 65535 / 4; rectangular maps)
+    L.small = (W + 1) <= tl::kSmallMaxRow && (H + 1) <= tl::kSmallMaxRow && (long long)L.n_nodes < (1ll << 22);
     const bool force_global = opt(TL_OPT_FORCE_GLOBAL_KERNEL) != 0;
     if (L.small) {
         L.slots = sm_count();
@@ -220,7 +221,6 @@ ScratchLayout make_scratch(int H, int W, int dim, bool with_sort, unsigned long 
 int check_shape(int B, int C, int H, int W, int feat_d) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(TL_ERR_ARG, "bad shape [%d,%d,%d,%d]", B, C, H, W);
     if (feat_d != 0 && feat_d != 1) return fail(TL_ERR_ARG, "feat_d must be 0 or 1 on 2-D maps, got %d", feat_d);
-    if (H != W) return fail(TL_ERR_ARG, "non-square maps are not supported (H=%d, W=%d)", H, W);
     if ((long long)(2 * H + 1) * (2 * W + 1) >= 0x7FFFFFF0LL) return fail(TL_ERR_ARG, "map too large");
     if ((long long)B * C > (1 << 24)) return fail(TL_ERR_ARG, "too many maps");
     return TL_OK;

@@ -133,11 +133,12 @@ def topo_loss_sharded(pred_local, true_local, lamda, interp=0, feat_d=2, loss_q=
             pred_local, true_local = torch.sigmoid(pred_local.float()), true_local.float()
         else:
             H, W = pred_local.shape[-2:]
-            if interp == 0 and H != W:
-                raise ValueError("non-square maps are not supported without interp (see topo_loss)")
-            S = int(interp) if interp != 0 else H
-            pred_local = _tl.resample(pred_local.float(), S, sigmoid=True)
-            true_local = _tl.resample(true_local.detach().float(), S, sigmoid=False)
+            if interp == 0 and H != W:  # nothing to resample (non-square maps: see topological_loss._canonical)
+                pred_local, true_local = torch.sigmoid(pred_local.float()), true_local.detach().float()
+            else:
+                S = int(interp) if interp != 0 else H
+                pred_local = _tl.resample(pred_local.float(), S, sigmoid=True)
+                true_local = _tl.resample(true_local.detach().float(), S, sigmoid=False)
             interp = 0
     if loss_fn is None:
         _tl._check_inputs(pred_local, true_local, feat_d)
@@ -152,6 +153,8 @@ def topo_loss_sharded(pred_local, true_local, lamda, interp=0, feat_d=2, loss_q=
             raise ValueError("B == C == 1: the reference crashes here")
         pred, truth = pred.reshape(C, 1, H, W), truth.reshape(C, 1, H, W)
         global_batch = C
+    if H != W:  # the reference reads the same flat buffer as W rows of H pixels (topological_loss._canonical)
+        pred, truth = pred.view(*pred.shape[:2], W, H), truth.view(*truth.shape[:2], W, H)
     # DDP divides the summed gradients by world: pre-multiply by world (mean over B_global / world images)
     scale = world if (grad_reduce == "mean" and world > 1) else 1
     if global_batch % scale:

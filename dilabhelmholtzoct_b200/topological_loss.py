@@ -192,7 +192,15 @@ def _canonical(pred, truth) -> Tuple[torch.Tensor, torch.Tensor]:
         raise ValueError("B == C == 1: the reference crashes here (batch_iter on a flat list)")
     if B == 1:
         pred, truth = pred.reshape(C, 1, H, W), truth.reshape(C, 1, H, W)
-    return pred.contiguous(), truth.contiguous()
+    pred, truth = pred.contiguous(), truth.contiguous()
+    if H != W:
+        # CubicalComplex passes ``dimensions=x.shape`` to gudhi un-reversed, and gudhi's FIRST dimension is the
+        # fastest-varying one [UPSTREAM-RECALL, SURVEY.md 8a row A3a]: for H != W the reference computes the
+        # persistence of the same flat buffer read as W rows of H pixels.  Flat indices -- hence where the
+        # gradient lands -- are unchanged, so the drop-in is a view (autograd undoes it).
+        lead = pred.shape[:2]
+        pred, truth = pred.view(*lead, W, H), truth.view(*lead, W, H)
+    return pred, truth
 
 
 def topo_loss(pred_obj, true_obj, lamda, interp=0, feat_d=2, loss_q=2, loss_r=False):
@@ -388,11 +396,12 @@ def topo_loss_from_logits(masks, gt_masks, lamda, interp=0, feat_d=2, loss_q=2, 
     if feat_d not in (0, 1):
         raise ValueError("feat_d must be 0 or 1 for 2-D maps (the reference call site uses feat_d=1)")
     H, W = masks.shape[-2:]
-    if interp == 0 and H != W:
-        raise ValueError("non-square maps are not supported without interp (see topo_loss)")
-    S = int(interp) if interp != 0 else H
-    pred = resample(masks.float(), S, sigmoid=True)
-    truth = resample(gt_masks.detach().float(), S, sigmoid=False)
+    if interp == 0 and H != W:  # nothing to resample; H != W as the reference sees such maps, see _canonical
+        pred, truth = torch.sigmoid(masks.float()), gt_masks.detach().float()
+    else:
+        S = int(interp) if interp != 0 else H
+        pred = resample(masks.float(), S, sigmoid=True)
+        truth = resample(gt_masks.detach().float(), S, sigmoid=False)
     pred, truth = _canonical(pred, truth)
     return _TopoLossFn.apply(pred, truth, lamda, feat_d, loss_q, loss_r, 0)
 
@@ -457,6 +466,8 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
         orig_shape = (B, C, H, W)
         pred_host, true_host = pred_host.reshape(C, 1, H, W), true_host.reshape(C, 1, H, -1)
         B, C = C, 1
+    # H != W: the reference reads the same flat buffer as W rows of H pixels (see _canonical)
+    Hk, Wk = (W, H) if H != W else (H, W)
     L = _lib.lib()
     # The persistence kernel runs one prediction map per SM at a time, so a group of `sms // C` images is one
     # full wave: finer groups would only add partly filled waves.  `chunks` caps the number of groups.
@@ -492,7 +503,7 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
                 events.append(ev)
         # forward and backward of a group run back to back on this stream, so ONE state buffer (sized for the
         # largest group) and the cached scratch serve every group
-        state, scratch = _buffers(max(bounds[i + 1] - bounds[i] for i in range(chunks)), C, H, W, feat_d, dev)
+        state, scratch = _buffers(max(bounds[i + 1] - bounds[i] for i in range(chunks)), C, Hk, Wk, feat_d, dev)
         for i in range(chunks):
             a, b = bounds[i], bounds[i + 1]
             cur.wait_event(events[i])
@@ -501,7 +512,7 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
                                                  cur.cuda_stream), "tl_unpack_mask_bits")
             elif truth_u8 is not None:  # ... as bytes: widen them on the device
                 truth[a:b].copy_(truth_u8[a:b])
-            args = (pred[a:b].data_ptr(), truth[a:b].data_ptr(), b - a, C, H, W, feat_d, float(loss_q),
+            args = (pred[a:b].data_ptr(), truth[a:b].data_ptr(), b - a, C, Hk, Wk, feat_d, float(loss_q),
                     float(lamda), int(bool(loss_r)), B, state.data_ptr(), state.numel(),
                     scratch.data_ptr(), scratch.numel(), parts[i:].data_ptr())
             if want_grad:  # loss and gradient of the group in one launch sequence
@@ -521,14 +532,21 @@ def topo_loss_from_host(pred_host, true_host, lamda, interp=0, feat_d=2, loss_q=
 
 # ---------------------------------------------------------------- inner boundaries (parity tests)
 
-def persistence_pairs(maps: torch.Tensor, dim: int) -> List[torch.Tensor]:
+def persistence_pairs(maps: torch.Tensor, dim: int, reference_shape_order: bool = False) -> List[torch.Tensor]:
     """CubicalComplex(dim=2, superlevel=False) on ``[..., H, W]`` maps: per map an int32 ``[K, 2]``
     tensor of (creator, destroyer) flat pixel indices in gudhi's emission order; for ``dim == 0`` the
     essential class, paired with ``argmax``, comes last (torch_topological
-    CubicalComplex._extract_generators_and_diagrams; reference call topological_loss.py:62)."""
+    CubicalComplex._extract_generators_and_diagrams; reference call topological_loss.py:62).
+
+    By default the map is the image it looks like (H rows of W pixels).  ``reference_shape_order=True``
+    reproduces what torch_topological computes for H != W, where gudhi receives ``dimensions=x.shape``
+    un-reversed and reads the flat buffer as W rows of H pixels (see ``_canonical``); flat indices are the
+    same in both readings, and for square maps the flag changes nothing."""
     if not maps.is_cuda or maps.dtype != torch.float32:
         raise ValueError("persistence_pairs expects float32 CUDA maps")
     H, W = maps.shape[-2:]
+    if reference_shape_order:
+        H, W = W, H
     flat = maps.reshape(-1, H, W).contiguous()
     n = flat.shape[0]
     L = _lib.lib()

@@ -29,6 +29,12 @@
  *     complex (gudhi T-construction), sublevel filtration, as CubicalComplex(dim=2,
  *     superlevel=False) at topological_loss.py:55-58.
  *   - persistence pairs are (creator pixel, destroyer pixel) flat C-order indices r*W+c.
+ *   - H and W are the map's geometry AS gudhi SEES IT: H rows of W pixels, W the fastest axis.  For
+ *     square maps that is the tensor's own shape.  For H != W, torch_topological hands gudhi
+ *     `dimensions=x.shape` un-reversed while gudhi's first dimension is the fastest one, so the
+ *     reference computes the persistence of the SAME flat buffer read as W rows of H pixels: a
+ *     caller that wants the reference's result for a [.., h, w] tensor passes H = w, W = h (flat
+ *     indices, and therefore the gradient layout, are unchanged).  The Python shim does this.
  *   - no CPU fallback exists: without a CUDA device every compute entry point fails.
  */
 #ifndef TOPOLOSS_H_

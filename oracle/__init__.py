@@ -79,12 +79,21 @@ def wasserstein(D1, D2, q: float = 2.0):
     return c, m[:len(D1)].copy()
 
 
-def topo_loss(pred, truth, lamda, feat_d=1, loss_q=2, loss_r=False, nthreads=1, want_grad=True):
+def topo_loss(pred, truth, lamda, feat_d=1, loss_q=2, loss_r=False, nthreads=1, want_grad=True,
+              reference_shape_order=True):
     """Forward + backward of /root/reference/octsam/models/topological_loss.py:11-96 (interp=0)
-    on [B,C,H,W] fp32 arrays.  Returns (loss, grad_pred or None, pair_counts[B*C,2])."""
+    on [B,C,H,W] fp32 arrays.  Returns (loss, grad_pred or None, pair_counts[B*C,2]).
+    ``reference_shape_order=False`` reads non-square maps as the images they look like (H rows of W pixels)
+    instead of the way the reference does (see below); it changes nothing for H == W."""
     pred = np.ascontiguousarray(pred, dtype=np.float32)
     truth = np.ascontiguousarray(truth, dtype=np.float32)
     B, C, H, W = pred.shape
+    if H != W and reference_shape_order:
+        # torch_topological's CubicalComplex hands gudhi ``dimensions=x.shape`` un-reversed although gudhi's first
+        # dimension is the fastest-varying one [UPSTREAM-RECALL; SURVEY.md 8a row A3a]: for H != W the reference
+        # computes the persistence of the same flat buffer read as W rows of H pixels.  Flat indices (and the
+        # gradient layout) are unchanged.  `cubical_pairs` keeps the plain reading (H rows of W pixels).
+        H, W = W, H
     loss = np.zeros(1, dtype=np.float32)
     grad = np.empty_like(pred) if want_grad else None
     cnt = np.zeros((B * C, 2), dtype=np.int32)

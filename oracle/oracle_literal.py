@@ -45,6 +45,19 @@ from __future__ import annotations
 import numpy as np
 
 
+def gudhi_bitmap_as_image(top_dimensional_cells, dimensions) -> np.ndarray:
+    """gudhi ``Bitmap_cubical_complex_base(dimensions, top_dimensional_cells)``: cell k of the flat list sits at
+    coordinates ``(k % dimensions[0], k // dimensions[0])`` -- the FIRST dimension is the fastest-varying one
+    [UPSTREAM-RECALL].  Returned as the 2-D image whose raster order is the flat order: ``dimensions[1]`` rows of
+    ``dimensions[0]`` pixels.  torch_topological's ``CubicalComplex._forward`` calls it with
+    ``dimensions=x.shape, top_dimensional_cells=x.flatten()``, i.e. un-reversed: an H x W tensor is read as W rows
+    of H pixels (nothing changes for H == W); the indices ``cofaces_of_persistence_pairs`` returns count cells in
+    the same flat order, so ``x.ravel()[idx]`` and ``np.unravel_index(idx, x.shape)`` address the tensor's own
+    pixels."""
+    d0, d1 = int(dimensions[0]), int(dimensions[1])
+    return np.asarray(top_dimensional_cells).reshape(d1, d0)
+
+
 def _cells(f: np.ndarray):
     """Doubled grid: values (min of cofaces), dims, positions.  SURVEY.md appendix C steps 1-2."""
     H, W = f.shape

@@ -39,6 +39,8 @@ def images():
         for size in (5, 8, 12, 24):
             f = rng.random((size, size)) if levels == 0 else rng.integers(0, levels, (size, size)) / levels
             out.append((f"rand_l{levels}_s{size}", f.astype(np.float32)))
+    for shape in ((4, 9), (9, 4), (6, 16)):  # non-square: read by gudhi as W rows of H pixels (shape passed un-reversed)
+        out.append((f"rect_{shape[0]}x{shape[1]}", rng.random(shape).astype(np.float32)))
     return out
 
 
@@ -53,6 +55,11 @@ def loss_cases():
     pred = rng.random((2, 2, 40, 40)).astype(np.float32)
     truth = (rng.random((2, 2, 40, 40)) < 0.4).astype(np.float32)
     cases.append(dict(pred=pred, truth=truth, feat_d=1, q=2, lamda=0.1, interp=16))
+    # non-square maps without interp: CubicalComplex passes the shape un-reversed to gudhi
+    for (B, C, H, W), feat_d in (((2, 2, 8, 14), 1), ((2, 2, 14, 8), 0)):
+        pred = rng.random((B, C, H, W)).astype(np.float32)
+        truth = (rng.random((B, C, H, W)) < 0.4).astype(np.float32)
+        cases.append(dict(pred=pred, truth=truth, feat_d=feat_d, q=2, lamda=0.1, interp=0))
     return cases
 
 

@@ -49,7 +49,8 @@ def test_workspace_bytes_and_argument_errors():
     assert rc == 0 and ns2 < ns and nc2 < nc
     assert _ws(L, 2, 14, 50, 50, 2)[0] == -1      # feat_d = 2 is invalid on 2-D maps
     assert b"feat_d" in L.tl_last_error()
-    assert _ws(L, 2, 14, 50, 60, 1)[0] == -1      # non-square
+    assert _ws(L, 2, 14, 50, 60, 1)[0] == 0       # rectangular maps are fine (H rows of W pixels)
+    assert _ws(L, 2, 14, 496, 512, 1)[0] == 0
     assert _ws(L, 0, 14, 50, 50, 1)[0] == -1
     assert L.tl_max_pairs(256, 256, 1) == 256 * 256 // 2 + 2
     with pytest.raises(ValueError):

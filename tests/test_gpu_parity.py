@@ -30,8 +30,6 @@ def _assert_same_pairs(maps, dim):
 def test_kats(name):
     img, h0, h1, ess = KATS[name]
     f = np.array(img, dtype=np.float32)
-    if f.shape[0] != f.shape[1]:
-        pytest.skip("non-square maps are rejected by the CUDA path")
     g0 = _gpu_pairs(f[None], 0)[0]
     g1 = _gpu_pairs(f[None], 1)[0]
     assert sorted(map(tuple, g0[:-1].tolist())) == sorted(h0)
@@ -608,3 +606,75 @@ def test_fused_gradient_equals_separate_launch():
     p.grad = None
     loss.backward()
     assert np.abs(p.grad.cpu().numpy() - g0).max() <= 1e-6 * np.abs(g0).max()
+
+
+# ---- rectangular maps.  The C ABI takes the geometry gudhi sees (H rows of W pixels); for H != W the
+#      reference reads the flat buffer as W rows of H pixels (torch_topological passes the shape un-reversed),
+#      which the shim and the oracle's topo_loss both reproduce
+@pytest.mark.parametrize("dim", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 7), (7, 2), (5, 9), (37, 53), (64, 200), (200, 64), (31, 255), (255, 32)])
+def test_pairs_rectangular(dim, shape):
+    rng = np.random.default_rng(7000 + shape[0] * 1000 + shape[1])
+    maps = rng.random((4,) + shape).astype(np.float32)
+    maps[1] = np.round(maps[1] * 6) / 6       # tie-heavy
+    maps[2] = (maps[2] > 0.45).astype(np.float32)  # two-valued
+    _assert_same_pairs(maps, dim)
+
+
+@pytest.mark.parametrize("dim", [0, 1])
+@pytest.mark.parametrize("shape", [(120, 600), (600, 120), (130, 510), (496, 512)])
+def test_pairs_rectangular_multi_band(dim, shape):
+    """more than 65536 pixels: column bands of a rectangular map (fast front end for W % 4 == 0, generic otherwise)"""
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(1, shape[0], shape[1], seed=4100 + shape[1], n_classes=5)
+    rng = np.random.default_rng(shape[0])
+    maps = np.stack([pred[0, 1].numpy(), truth[0, 3].numpy(), rng.random(shape).astype(np.float32)])
+    _assert_same_pairs(maps, dim)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 40, 56), (2, 3, 56, 40), (3, 1, 24, 40)])
+@pytest.mark.parametrize("feat_d", [0, 1])
+def test_loss_rectangular_follows_the_reference_shape_order(shape, feat_d):
+    import dilabhelmholtzoct_b200 as tlb
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    B, C, H, W = shape
+    pred, truth = make_batch(B, H, W, seed=91 + H, n_classes=C)
+    _check_loss(pred, truth, 0.1, feat_d)
+    # the same thing said the long way: the loss of the flat buffers read as W rows of H pixels
+    want, wgrad, _ = oracle.topo_loss(pred.numpy().reshape(B, C, W, H), truth.numpy().reshape(B, C, W, H), 0.1, feat_d=feat_d,
+                                      reference_shape_order=False)
+    loss, grad = _loss_and_grad(pred, truth, 0.1, feat_d=feat_d)
+    assert grad.shape == (B, C, H, W)
+    assert abs(loss - want) <= REL * abs(want) + 1e-12
+    assert np.abs(grad.reshape(B, C, W, H) - wgrad).max() <= REL * np.abs(wgrad).max() + 1e-12
+    # pairs at the inner boundary: plain reading by default, the reference's reading on request
+    f = pred[0, 0].numpy()
+    got = tlb.persistence_pairs(pred[0, 0].cuda(), 1, reference_shape_order=True)[0].cpu().numpy()
+    assert np.array_equal(got, oracle.cubical_pairs(f.reshape(W, H), 1))
+
+
+def test_rectangular_host_api_and_logits_call():
+    import dilabhelmholtzoct_b200 as tlb
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(3, 48, 64, seed=17, n_classes=4)
+    want, wgrad, _ = oracle.topo_loss(pred.numpy(), truth.numpy(), 0.1, feat_d=1)
+    loss, grad = tlb.topo_loss_from_host(pred.pin_memory(), tlb.pack_mask_bits(truth), 0.1, feat_d=1, truth_packed=True, chunks=2)
+    assert abs(float(loss) - want) <= REL * abs(want)
+    assert grad.shape == pred.shape and np.abs(grad.cpu().numpy() - wgrad).max() <= REL * np.abs(wgrad).max()
+    logits = torch.logit(pred.clamp(1e-4, 1 - 1e-4)).cuda().requires_grad_(True)
+    l2 = tlb.topo_loss_from_logits(logits, truth.cuda(), 0.1, feat_d=1)
+    l2.backward()
+    w2, _, _ = oracle.topo_loss(torch.sigmoid(logits.detach()).cpu().numpy(), truth.numpy(), 0.1, feat_d=1)
+    assert abs(float(l2) - w2) <= REL * abs(w2) and logits.grad.shape == logits.shape
+
+
+def test_rectangular_batch_of_one():
+    """B == 1 (every channel its own image) and H != W together"""
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(1, 24, 40, seed=5, n_classes=4)
+    loss, grad = _loss_and_grad(pred, truth, 0.1, feat_d=1)
+    want, wgrad, _ = oracle.topo_loss(pred.permute(1, 0, 2, 3).contiguous().numpy(),
+                                      truth.permute(1, 0, 2, 3).contiguous().numpy(), 0.1, feat_d=1)
+    assert abs(loss - want) <= REL * abs(want)
+    assert grad.shape == (1, 4, 24, 40)
+    assert np.abs(grad - wgrad.transpose(1, 0, 2, 3)).max() <= REL * np.abs(wgrad).max()

@@ -169,7 +169,6 @@ def test_betti_curves_match_connected_component_counts(seed, levels):
     from scipy import ndimage
     rng = np.random.default_rng(100 + seed)
     H, W = int(rng.integers(6, 20)), int(rng.integers(6, 20))
-    H = W  # square maps only on this path
     f = rng.random((H, W)).astype(np.float32)
     if levels:
         f = (np.floor(f * levels) / levels).astype(np.float32)
@@ -254,3 +253,25 @@ def test_two_valued_h1_rule():
                 got.append((p + n, p))
         got.sort(key=lambda x: x[1])
         assert [tuple(x) for x in want.tolist()] == got
+
+
+def test_nonsquare_maps_follow_the_reference_shape_order():
+    """torch_topological passes ``dimensions=x.shape`` un-reversed to gudhi, whose first dimension is the fastest
+    one: an H x W map (H != W) is read as W rows of H pixels.  The oracle's topo_loss reproduces that; flat indices
+    and the gradient layout are unchanged; square maps are untouched."""
+    from oracle import oracle_literal as L
+    rng = np.random.default_rng(3)
+    x = rng.random((3, 5)).astype(np.float32)
+    img = L.gudhi_bitmap_as_image(x.ravel(), x.shape)
+    assert img.shape == (5, 3) and np.array_equal(img.ravel(), x.ravel())
+    sq = rng.random((4, 4)).astype(np.float32)
+    assert np.array_equal(L.gudhi_bitmap_as_image(sq.ravel(), sq.shape), sq)
+    pred = rng.random((2, 2, 6, 10)).astype(np.float32)
+    truth = (rng.random((2, 2, 6, 10)) > 0.5).astype(np.float32)
+    l1, g1, _ = oracle.topo_loss(pred, truth, 0.1, feat_d=1)
+    l2, g2, _ = oracle.topo_loss(pred.reshape(2, 2, 10, 6), truth.reshape(2, 2, 10, 6), 0.1, feat_d=1, reference_shape_order=False)
+    assert l1 == l2 and g1.shape == pred.shape and np.array_equal(g1.ravel(), g2.ravel())
+    # ... and it is NOT the loss of the transposed or of the plainly read image in general
+    pairs_plain = oracle.cubical_pairs(pred[0, 0], 1)
+    pairs_ref = oracle.cubical_pairs(L.gudhi_bitmap_as_image(pred[0, 0].ravel(), pred[0, 0].shape), 1)
+    assert pairs_plain.shape != pairs_ref.shape or not np.array_equal(pairs_plain, pairs_ref)

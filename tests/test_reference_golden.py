@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import oracle
+from oracle.oracle_literal import gudhi_bitmap_as_image
 
 FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.json")
 needs_fixture = pytest.mark.skipif(not os.path.exists(FIXTURE), reason="reference deps absent (no reference_vectors.json)")
@@ -28,6 +29,9 @@ def _as_sets(pairs):
 def test_oracle_pairs_equal_the_reference():
     for case in _doc()["pairs"]:
         f = np.array(case["image"], dtype=np.float32)
+        # CubicalComplex hands gudhi the shape un-reversed: a non-square map is read as W rows of H pixels
+        # (oracle_literal.gudhi_bitmap_as_image); flat indices are those of the tensor either way
+        f = gudhi_bitmap_as_image(f.ravel(), f.shape)
         for dim in (0, 1):
             got = oracle.cubical_pairs(f, dim).tolist()
             want = case[f"h{dim}"]
@@ -69,11 +73,10 @@ def test_cuda_path_equals_the_reference():
     doc = _doc()
     for case in doc["pairs"]:
         f = np.array(case["image"], dtype=np.float32)
-        if f.shape[0] != f.shape[1]:
-            continue
         x = torch.tensor(f, device="cuda")[None]
         for dim in (0, 1):
-            assert tlb.persistence_pairs(x, dim)[0].cpu().tolist() == case[f"h{dim}"], (case["name"], dim)
+            got = tlb.persistence_pairs(x, dim, reference_shape_order=True)[0].cpu().tolist()
+            assert got == case[f"h{dim}"], (case["name"], dim)
     for case in doc["losses"]:
         p = torch.tensor(case["pred"], device="cuda", requires_grad=True)
         loss = tlb.topo_loss(p, torch.tensor(case["truth"], device="cuda"), case["lamda"], interp=case["interp"],
