@@ -228,7 +228,9 @@ def test_errors_and_early_out():
     with pytest.raises(ValueError):
         tlb.topo_loss(x.cpu(), x.cpu(), 0.1, feat_d=1)  # no CPU fallback
     with pytest.raises(ValueError):
-        tlb.topo_loss(torch.rand((2, 2, 8, 9), device="cuda"), torch.rand((2, 2, 8, 9), device="cuda"), 0.1, feat_d=1)
+        tlb.topo_loss(torch.rand((2, 2, 8, 9), device="cuda"), torch.rand((2, 2, 9, 8), device="cuda"), 0.1, feat_d=1)  # shapes differ
+    with pytest.raises(ValueError):
+        tlb.topo_loss(torch.rand((2, 2, 8, 1), device="cuda"), torch.rand((2, 2, 8, 1), device="cuda"), 0.1, feat_d=1)  # squeezed away
     with pytest.raises(ValueError):
         tlb.topo_loss(x[:1, :1], x[:1, :1], 0.1, feat_d=1)
 
