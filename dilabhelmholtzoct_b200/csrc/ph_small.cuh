@@ -114,6 +114,10 @@ struct __align__(16) CrossEdge {
 __device__ __forceinline__ void store_edge(CrossEdge* p, uint64_t skey, uint32_t la, uint32_t lb) {
     *reinterpret_cast<uint4*>(p) = make_uint4((uint32_t)skey, (uint32_t)(skey >> 32), la, lb);
 }
+// ... with an L2 eviction policy (TL_OPT_LIST_MODE bit 1)
+__device__ __forceinline__ void store_edge_hint(CrossEdge* p, uint64_t skey, uint32_t la, uint32_t lb, uint64_t policy) {
+    stg_v4_hint(p, make_uint4((uint32_t)skey, (uint32_t)(skey >> 32), la, lb), policy);
+}
 
 // dense edge id -> pixel that gudhi's coface walk reaches from that edge
 template <int DIM>
@@ -468,6 +472,7 @@ struct PhSmallArgs {
     size_t k_stride;
     unsigned long long* prof;  // optional [8] phase cycle counters
     int binary_path;           // 1: try the two-valued fast path first (H1)
+    int list_mode;             // TL_OPT_LIST_MODE: L2 treatment of the crossing-edge list (single-band maps)
     // tl_forward only: the SM that completes a map's second diagram writes the map's cost itself when one of the two
     // diagrams is empty (ready[k] = 4), else hands the map (ready[k] = 3) to the CTAs that have run out of persistence
     // jobs: the matching runs in the tail of this launch instead of a launch of its own
@@ -549,7 +554,10 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
     __shared__ double s_red[kPhThreads / 32];
     __shared__ unsigned long long s_base;
     const PhArgs& A = S.base;
-    const uint64_t l2_keep = l2_policy_evict_last();
+    // (single-band kernel only: TL_OPT_LIST_MODE bit 2 reads the maps without the evict-last hint, bit 1 stores the list with it)
+    const bool list_keep = !MULTI && (S.list_mode & 2) != 0;
+    const uint64_t l2_last = l2_policy_evict_last();
+    const uint64_t l2_keep = (!MULTI && (S.list_mode & 4)) ? l2_policy_evict_normal() : l2_last;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int H = A.H, W = A.W, N = H * W;
     uint16_t* par = reinterpret_cast<uint16_t*>(smem);
@@ -1086,7 +1094,10 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
                                 else if (e == 1) { lo = ulab[k]; pos = (uint32_t)(r * GWb + cl + k); val = r == 0 ? fp : fminf(u[k], fp); }
                                 else if (e == 2) { lo = 0u; pos = (uint32_t)(r * GWb + 2 * bw); val = fp; }
                                 else { lo = 0u; pos = (uint32_t)(H * GWb + cl + k); val = fp; }
-                                if (slot < (int)S.e_stride) store_edge(elist + slot, g.make_ekey(val, pos), lo, own);
+                                if (slot < (int)S.e_stride) {
+                                    if (list_keep) store_edge_hint(elist + slot, g.make_ekey(val, pos), lo, own, l2_last);
+                                    else store_edge(elist + slot, g.make_ekey(val, pos), lo, own);
+                                }
                                 ++slot;
                             }
                         }
@@ -1410,6 +1421,14 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
         if (tid == 0) { atomicAdd(&g_stats[6], (unsigned long long)K); atomicAdd(&g_stats[7], 1ull); }
 #endif
         __syncthreads();
+        // the list has been consumed and is scratch: let L2 drop its lines instead of writing them back (TL_OPT_LIST_MODE
+        // bit 0).  Whole 128-byte lines of this CTA's own slot only (slots are multiples of 1 KB)
+        if (!MULTI && (S.list_mode & 1)) {
+            const int n_lines = (min(s_ncross, (int)S.e_stride) * (int)sizeof(CrossEdge) + 127) >> 7;
+            const char* lb_ = reinterpret_cast<const char*>(elist);
+            if ((reinterpret_cast<uintptr_t>(lb_) & 127) == 0)
+                for (int i = tid; i < n_lines; i += nt) l2_discard_line(lb_ + (size_t)i * 128);
+        }
         TL_PROF(4);
 
         // ---- emit: every thread owns a contiguous run of basins, so ONE block scan yields

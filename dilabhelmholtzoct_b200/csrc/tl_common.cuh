@@ -104,6 +104,20 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// 128-bit store with an L2 eviction policy
+__device__ __forceinline__ void stg_v4_hint(void* ptr, uint4 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy) : "memory");
+}
+// The 128-byte line at `ptr` (128-byte aligned) holds nothing anybody will read again: L2 may drop it without
+// writing it back to DRAM
+__device__ __forceinline__ void l2_discard_line(const void* ptr) {
+    asm volatile("discard.global.L2 [%0], 128;" :: "l"(ptr) : "memory");
+}
 __device__ __forceinline__ float4 ldg_f4_keep(const float4* ptr, uint64_t policy) {
     float4 v;
     asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(policy));

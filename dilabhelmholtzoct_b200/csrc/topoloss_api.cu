@@ -37,6 +37,7 @@ int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(TL_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
+constexpr int kListModeDefault = 0;  // TL_OPT_LIST_MODE when the environment does not say
 // Process-wide options (tl_set_option); initial values come from the environment ONCE, at load time.
 struct Options {
     std::atomic<int> v[TL_OPT_COUNT_];
@@ -48,6 +49,8 @@ struct Options {
         v[TL_OPT_WORST_CASE_WORKSPACE] = env1("TL_WORST_CASE_WORKSPACE");
         v[TL_OPT_NO_FUSED_MATCH] = env1("TL_NO_FUSED_MATCH");
         v[TL_OPT_NO_FUSED_GRAD] = env1("TL_NO_FUSED_GRAD");
+        const char* lm = getenv("TL_LIST_MODE");
+        v[TL_OPT_LIST_MODE] = lm ? atoi(lm) : kListModeDefault;
     }
 };
 Options g_opt;
@@ -276,6 +279,7 @@ int launch_ph(const float* m0, const float* m1, int n_sets, int M, const tl::Pai
         sa.elist = at<tl::CrossEdge>(scratch, L.elist); sa.e_stride = L.e_stride;
         sa.prof = opt(TL_OPT_PROFILE) ? at<unsigned long long>(state, 64) : nullptr;
         sa.binary_path = !opt(TL_OPT_NO_BINARY_PATH);
+        sa.list_mode = opt(TL_OPT_LIST_MODE);
         sa.fuse_match = mf != nullptr && !opt(TL_OPT_NO_FUSED_MATCH);
         sa.ready = ready;
         sa.fuse_grad = 0;

@@ -72,7 +72,11 @@ const char* tl_last_error(void);
 #define TL_OPT_WORST_CASE_WORKSPACE 3 /* size every table for the worst case: no input can overflow */
 #define TL_OPT_NO_FUSED_MATCH 4       /* measurement: matching in a launch of its own instead of the persistence kernel's tail */
 #define TL_OPT_NO_FUSED_GRAD 5        /* measurement: tl_forward_backward writes the gradient in a launch of its own */
-#define TL_OPT_COUNT_ 6
+#define TL_OPT_LIST_MODE 6            /* measurement (env TL_LIST_MODE, an integer): L2 treatment of the per-CTA crossing-edge list of
+                                         single-band maps.  bit 0: discard the list's L2 lines once the merge has consumed them (no
+                                         write-back of scratch data); bit 1: store the list with an evict-last policy; bit 2: read
+                                         the maps without the evict-last hint */
+#define TL_OPT_COUNT_ 7
 int tl_set_option(int which, int value);
 int tl_get_option(int which);
 
