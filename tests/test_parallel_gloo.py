@@ -18,7 +18,9 @@ class _OracleLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, truth, lamda, feat_d, q, loss_r, gb):
         B = pred.shape[0]
-        loss, grad, _ = oracle.topo_loss(pred.detach().numpy(), truth.numpy(), lamda, feat_d=feat_d, loss_q=q, loss_r=loss_r)
+        # kernel semantics: the maps are the geometry they come in (the wrapper has already exchanged H and W of non-square maps)
+        loss, grad, _ = oracle.topo_loss(pred.detach().contiguous().numpy(), truth.contiguous().numpy(), lamda, feat_d=feat_d,
+                                         loss_q=q, loss_r=loss_r, reference_shape_order=False)
         ctx.grad = torch.tensor(grad) * (B / gb)
         return torch.tensor(loss * B / gb)
 
@@ -142,3 +144,19 @@ def test_single_process_wrapper_matches_oracle_and_handles_global_batch_one():
                                   truth.permute(1, 0, 2, 3).contiguous().numpy(), 0.1, feat_d=1)
     assert abs(float(loss) - want) <= 1e-6 * abs(want)
     assert topo_loss_sharded(pred, truth, 0.0) == 0.0
+
+
+def test_wrapper_reads_non_square_maps_like_the_reference():
+    """H != W: the wrapper hands the op the flat buffers as W rows of H pixels; the gradient comes
+    back in the caller's layout"""
+    from dilabhelmholtzoct_b200.parallel import topo_loss_sharded
+    rng = np.random.default_rng(6)
+    pred = torch.tensor(rng.random((2, 2, 8, 14)).astype(np.float32), requires_grad=True)
+    truth = torch.tensor((rng.random((2, 2, 8, 14)) < 0.4).astype(np.float32))
+    loss = topo_loss_sharded(pred, truth, 0.1, feat_d=1, loss_fn=_oracle_fn)
+    loss.backward()
+    want, wgrad, _ = oracle.topo_loss(pred.detach().numpy(), truth.numpy(), 0.1, feat_d=1)  # the reference's reading
+    assert abs(float(loss) - want) <= 1e-6 * abs(want)
+    assert pred.grad.shape == pred.shape and np.allclose(pred.grad.numpy(), wgrad, rtol=1e-6, atol=1e-9)
+    plain, _, _ = oracle.topo_loss(pred.detach().numpy(), truth.numpy(), 0.1, feat_d=1, reference_shape_order=False)
+    assert abs(plain - want) > 1e-6 * abs(want)  # ... which is not the loss of the maps read as they look
