@@ -202,8 +202,29 @@ constexpr int kRefillIdle = TL_REFILL_TH;  // idle lanes that trigger a refill o
 #define TL_FLAT2 1
 #endif
 #ifndef TL_HOPS
-#define TL_HOPS 3
+#define TL_HOPS 4   // 3 -> 4: -0.8 % on the C2 step (2 / 5 / 6 / 8: +4.5 / -0.1 / +0.5 / +2.1 %; scripts/gpu_r2j.sh)
 #endif
+// unroll factors of the fast front end's trip loops (experiments; 1 = as written)
+#ifndef TL_UNROLL_L0
+#define TL_UNROLL_L0 1
+#endif
+constexpr int kUnrollL0 = TL_UNROLL_L0;
+#ifndef TL_UNROLL_FLATTEN
+#define TL_UNROLL_FLATTEN 1
+#endif
+constexpr int kUnrollFlatten = TL_UNROLL_FLATTEN;
+#ifndef TL_UNROLL_CENSUS
+#define TL_UNROLL_CENSUS 1
+#endif
+constexpr int kUnrollCensus = TL_UNROLL_CENSUS;
+#ifndef TL_UNROLL_LABEL
+#define TL_UNROLL_LABEL 1
+#endif
+constexpr int kUnrollLabel = TL_UNROLL_LABEL;
+#ifndef TL_UNROLL_COMPACT
+#define TL_UNROLL_COMPACT 1
+#endif
+constexpr int kUnrollCompact = TL_UNROLL_COMPACT;
 constexpr int kHopsPerIter = TL_HOPS;
 constexpr int kRing = 64;  // edges per warp in the shared staging ring (two cp.async batches of 32)
 
@@ -807,6 +828,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
             {
                 float vlo = __int_as_float(0x7F800000), vhi = __int_as_float(0xFF800000);
                 bool nan_seen = false;
+#pragma unroll kUnrollL0
                 for (int t = 0; t < trips; ++t) {
                     const int x = wbeg + t * 128 + lane * 4;  // band-local id of the quad
                     unsigned defer = 0u;
@@ -896,6 +918,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
                 int pending = 0;
                 // bottom rows first: most ties point DOWN (plateaus), so a row that jumps after the rows below it
                 // sees their already shortened pointers and a vertical run collapses within one round
+#pragma unroll kUnrollFlatten
                 for (int t = trips - 1; t >= 0; --t) {
                     const int x = wbeg + t * 128 + lane * 4;
                     const bool act = x < wend && ((donebits >> (4 * t)) & 15ull) != 15ull;
@@ -946,6 +969,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
             const int Kb = s_K;  // basins of this band: global ids cid_base+1 .. cid_base+Kb
             {
                 int run = s_wcnt[warp];
+#pragma unroll kUnrollCensus
                 for (int t = 0; t < trips; ++t) {
                     const int x = wbeg + t * 128 + lane * 4;
                     const unsigned nib = (unsigned)(rootbits >> (4 * t)) & 15u;
@@ -985,6 +1009,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
             __syncthreads();
             // per-node label in place: band-local basin rank + 1, 0 for OUTSIDE's basin.  Root entries are labels already;
             // every other entry holds its root's index, or kOut16, whose entry is OUTSIDE's label: one load, no test
+#pragma unroll kUnrollLabel
             for (int t = 0; t < trips; ++t) {
                 const int x = wbeg + t * 128 + lane * 4;
                 unsigned nib = (unsigned)(rootbits >> (4 * t)) & 15u;
@@ -1011,6 +1036,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) ph_small_kernel(const __grid_co
             auto glab = [&](uint32_t v) { return v ? (uint32_t)cid_base + v : 0u; };  // band-local label -> map-wide label
             auto llab = [&](uint32_t v) { return v; };
             const int GWb = 2 * bw + 1;
+#pragma unroll kUnrollCompact
             for (int t = 0; t < trips; ++t) {  // warp-uniform trip count
                 const int x = wbeg + t * 128 + lane * 4;
                 const bool valid = x < wend;

@@ -47,6 +47,10 @@ for m in MODES:
     g = p.grad.clone()
     if ref is None:
         ref = (loss.clone(), g)
-    same = bool(torch.equal(loss, ref[0])) and bool(torch.equal(g, ref[1]))
-    print(f"mode {m}: {best:.4f} ms/step (best of 3 x 20), loss {float(loss):.7f}, identical to mode {MODES[0]}: {same}", flush=True)
+    same_l, same_g = bool(torch.equal(loss, ref[0])), bool(torch.equal(g, ref[1]))
+    dg = float((g - ref[1]).abs().max()) / float(ref[1].abs().max())
+    print(f"mode {m}: {best:.4f} ms/step (best of 3 x 20), loss {float(loss.detach()):.7f}, vs the first mode: loss identical {same_l}, "
+          f"gradient identical {same_g} (max rel diff {dg:.2e}, support equal {bool(torch.equal(g != 0, ref[1] != 0))})", flush=True)
+    # fingerprint for comparisons ACROSS library variants (separate processes): exact loss bits, gradient support size, |g| sum
+    print(f"   fingerprint: loss {float(loss.detach()).hex()} nnz {int((g != 0).sum())} sum|g| {float(g.double().abs().sum()):.12e}", flush=True)
 tlb.check_status()

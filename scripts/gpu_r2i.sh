@@ -14,3 +14,7 @@ for k in sorted(per):
     d = per[k]
     print(k, {a.split("__")[1][:14]: round(v / 1e6, 2) for a, v in d.items()})
 P
+# compile-time merge knobs (variant libraries), mode 0 only
+for v in hops2 hops4 refill4 refill16; do
+  echo "== $v"; TL_LIB_PATH=$PWD/dilabhelmholtzoct_b200/libtopoloss_$v.so AB_MODES=0 timeout 100 python scripts/ab_list_mode.py 2>&1 | grep "^mode"
+done
