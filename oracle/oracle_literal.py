@@ -22,7 +22,8 @@ published algorithm of those libraries:
 * torch_topological ``CubicalComplex._extract_generators_and_diagrams`` -- the essential H0
   class is paired with ``argmax(x)``; diagram values are re-gathered from ``x``.
 
-It is O(cells^2)-ish and meant for maps up to ~32x32.
+Worst case O(cells^2), in practice seconds for a 256 x 256 map (tests/test_oracle.py checks the fast oracle against it
+at that size too).
 
 KNOWN RISK, H0 ONLY (unverifiable here): the persistence pairing of a TOTAL order is unique, and
 for H1 gudhi derives it from that order through its general cohomology reduction -- which is what this file

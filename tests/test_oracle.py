@@ -46,6 +46,24 @@ def test_fast_equals_literal(h, w, mode, seed):
     assert [tuple(x) for x in oracle.cubical_pairs(f, 1)] == l1
 
 
+@pytest.mark.parametrize("kind", ["pred", "truth", "ties32", "iid", "rect"])
+def test_fast_equals_literal_at_headline_size(kind):
+    """Oracle F (the checker of the GPU parity tests at full size) against the literal boundary-matrix reduction on
+    256 x 256 maps of BASELINE's workload -- incl. emission order -- and on a rectangular map."""
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, truth = make_batch(1, 256, 256, seed=1234)
+    rng = np.random.default_rng(11)
+    f = {"pred": lambda: pred[0, 3].numpy(), "truth": lambda: truth[0, 3].numpy(),
+         "ties32": lambda: (np.round(pred[0, 5].numpy() * 32) / 32).astype(np.float32),
+         "iid": lambda: rng.random((256, 256)).astype(np.float32),
+         "rect": lambda: rng.random((96, 200)).astype(np.float32)}[kind]()
+    l0, l1, ess = cubical_pairs_literal(f)
+    assert [tuple(x) for x in oracle.cubical_pairs(f, 0)] == l0 + [ess]
+    assert [tuple(x) for x in oracle.cubical_pairs(f, 1)] == l1
+    if kind != "truth":
+        assert len(l1) > 1000
+
+
 def _torch_cost_matrix(D1, D2, q):
     """torch_topological WassersteinDistance._make_distance_matrix, restated."""
     def proj(d):
