@@ -110,6 +110,32 @@ def test_wasserstein_is_the_exact_lp_optimum(q):
         assert abs(tot - cost) < 1e-6
 
 
+@pytest.mark.parametrize("q", [1, 2])
+def test_wasserstein_equals_the_literal_transport_lp(q):
+    """The reference's own formulation, literally: ``ot.emd2(a, b, M)`` on the (n+1) x (m+1) matrix with masses
+    a = [1]*n + [m], b = [1]*m + [n] (torch_topological WassersteinDistance.forward, called at
+    topological_loss.py:78-82) -- solved as a transport LP with scipy's HiGHS instead of POT's network simplex.  The
+    oracle (and the kernels) solve the equivalent partial assignment; this pins the equivalence."""
+    from scipy.optimize import linprog
+    rng = np.random.default_rng(40 + q)
+    for t in range(60):
+        n, m = int(rng.integers(0, 9)), int(rng.integers(0, 7))
+        D1, D2 = _diagrams(rng, n, m, t % 4 == 0)
+        cost, _ = oracle.wasserstein(D1, D2, q)
+        M = _torch_cost_matrix(torch.tensor(D1), torch.tensor(D2), q).double().numpy()
+        a = np.array([1.0] * n + [float(m)])
+        b = np.array([1.0] * m + [float(n)])
+        R, Cc = n + 1, m + 1
+        A_eq = np.zeros((R + Cc, R * Cc))
+        for i in range(R):
+            A_eq[i, i * Cc:(i + 1) * Cc] = 1.0          # row sums = a
+        for j in range(Cc):
+            A_eq[R + j, j::Cc] = 1.0                   # column sums = b
+        res = linprog(M.ravel(), A_eq=A_eq, b_eq=np.concatenate([a, b]), bounds=(0, None), method="highs")
+        assert res.status == 0
+        assert abs(res.fun - cost) < 1e-7 + 1e-7 * abs(cost), (n, m, res.fun, cost)
+
+
 def test_kat_w2_toy_and_gradient_tie():
     cost, match = oracle.wasserstein(np.array([[0.2, 0.8]], np.float32), np.array([[0.0, 1.0]], np.float32), 2)
     assert abs(cost - 0.04) < 1e-7 and match[0] == 0  # W = 0.2, not 0.34 via the diagonal
