@@ -338,7 +338,11 @@ def main():
         uuid = ""
     sampler = make_sampler(local_rank, uuid)
     if rank == 0:
-        sampler.start()
+        try:
+            sampler.start()
+        except Exception:
+            sampler = ClockSampler(local_rank)
+            sampler.start()
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize()
@@ -356,7 +360,12 @@ def main():
     for _ in range(3):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        try:
+            clocks = sampler.stop()
+        except Exception as e:  # the clock record must never cost the bench line
+            clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"sampler failed: {type(e).__name__}"]}
 
     if rank != 0:
         if world > 1:
