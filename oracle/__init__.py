@@ -8,6 +8,13 @@ PARITY UNPINNED: the reference's arithmetic for this path
 ``torch_topological`` / ``gudhi`` / ``POT``, which are not vendored, pinned or installed and the
 reference has no tests.  The oracle restates their published algorithms; ``oracle_literal``
 (boundary-matrix reduction of the literal cell complex) pins ``topo_oracle.c``.
+
+What IS pinned against the reference's own code: everything downstream of the persistence pairs.
+``tests/golden/make_golden_orchestration.py`` imports the unmodified
+``/root/reference/octsam/models/topological_loss.py`` (stand-ins for its absent imports in
+``tests/golden/ref_stubs``: the pairs come from this oracle, ``ot.emd2`` from scipy's LP solver, the rest is
+torch autograd) and records loss and gradient; ``tests/test_zz_orchestration_golden.py`` checks
+``topo_loss`` below against those vectors.  The pairs themselves (gudhi) remain unpinned.
 """
 from __future__ import annotations
 

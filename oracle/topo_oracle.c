@@ -10,6 +10,9 @@
  * SURVEY.md section 8c); the reference has no tests or golden vectors.  This file
  * restates their published algorithms and is pinned against oracle_literal.py (a
  * literal boundary-matrix reduction of the gudhi cell complex) and hand-derived KATs.
+ * to_wasserstein and to_topo_loss (everything downstream of the pairs) ARE pinned against
+ * the unmodified reference file run under torch autograd: tests/golden/orchestration_vectors.json
+ * (tests/golden/make_golden_orchestration.py); the pairs of to_cubical_pairs are not.
  *
  * What each function follows:
  *   to_cubical_pairs      gudhi Bitmap_cubical_complex (T-construction, order
