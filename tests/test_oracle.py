@@ -319,3 +319,26 @@ def test_nonsquare_maps_follow_the_reference_shape_order():
     pairs_plain = oracle.cubical_pairs(pred[0, 0], 1)
     pairs_ref = oracle.cubical_pairs(L.gudhi_bitmap_as_image(pred[0, 0].ravel(), pred[0, 0].shape), 1)
     assert pairs_plain.shape != pairs_ref.shape or not np.array_equal(pairs_plain, pairs_ref)
+
+
+def test_h0_tie_rule_candidates_agree_on_values_and_on_tie_free_maps():
+    """The two candidate rules for gudhi's dimension-0 pairing (canonical total order -- implemented everywhere here -- vs
+    the union-find short cut recalled from Persistent_cohomology::update_cohomology_groups_edge, DESIGN.md section 2):
+    identical pairs on maps without exactly tied values (fp32 sigmoid outputs), and on tie-heavy maps the same MULTISET of
+    (birth, death) values -- so the loss value never depends on the rule, only which of several equal-valued pixels
+    receives the gradient does."""
+    from oracle.oracle_literal import h0_pairs_gudhi_union_find
+    from dilabhelmholtzoct_b200.synthetic import make_batch
+    pred, _ = make_batch(1, 64, 64, seed=77, n_classes=4)
+    for levels in (0, 1024, 16):
+        f = pred[0, 1].numpy()
+        if levels:
+            f = (np.round(f * levels) / levels).astype(np.float32)
+        h0u, essu = h0_pairs_gudhi_union_find(f)
+        can = oracle.cubical_pairs(f, 0)
+        h0c, essc = [tuple(int(v) for v in x) for x in can[:-1]], tuple(int(v) for v in can[-1])
+        fl = f.ravel()
+        assert sorted((fl[a], fl[b]) for a, b in h0u) == sorted((fl[a], fl[b]) for a, b in h0c)
+        assert fl[essu[0]] == fl[essc[0]] and essu[1] == essc[1]
+        if not levels:
+            assert sorted(h0u) == sorted(h0c) and essu == essc
